@@ -1,0 +1,188 @@
+/*
+ * llama2_b200.h — C ABI of the B200 (sm_100a) decode hot path for cgbur/llama2.zig.
+ *
+ * This library replaces ONE internal call of the reference,
+ *     transformer(token, pos, &config, &state, &weights)      src/main.zig:285, call site :996
+ * and the numeric helpers it calls (src/main.zig:432-713).  The reference has no FFI of
+ * its own; these entry points are what its Zig host declares `extern "c"` (see
+ * INTEGRATION.md for the patch).  Everything else (CLI, checkpoint and tokenizer
+ * loaders, sampler) stays in the host.
+ *
+ * Conventions
+ *   - plain C types only; every call returns L2B_OK (0) or a negative l2b_status and never
+ *     aborts or throws across the boundary (the reference's `assert`s, e.g. :433-434,
+ *     :534-540, become argument checks);
+ *   - host pointers are borrowed for the duration of the call only;
+ *   - one context = one GPU; not thread-safe (the reference is single-threaded);
+ *   - there is NO CPU fallback: if no sm_100 device is usable the call fails with
+ *     L2B_ERR_CUDA / L2B_ERR_NO_DEVICE.
+ */
+#ifndef LLAMA2_B200_H
+#define LLAMA2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define L2B_ABI_VERSION 1
+
+typedef enum l2b_status {
+    L2B_OK = 0,
+    L2B_ERR_INVALID_ARG = -1,   /* NULL pointer, token/pos out of range, bad size          */
+    L2B_ERR_UNSUPPORTED = -2,   /* shape the kernels do not cover (see l2b_create)          */
+    L2B_ERR_CUDA = -3,          /* a CUDA runtime call failed; see l2b_last_error()         */
+    L2B_ERR_NO_DEVICE = -4,     /* no CUDA device / not compute capability 10.x             */
+    L2B_ERR_OOM = -5,           /* device or pinned-host allocation failed                  */
+    L2B_ERR_COMM = -6,          /* NCCL / peer-memory setup or collective failed            */
+    L2B_ERR_STATE = -7          /* call order violated (e.g. pos beyond what was appended)  */
+} l2b_status;
+
+/* Mirrors ConfigReader (src/main.zig:17-25) after main() has normalised it (:942-946):
+ * vocab_size is already abs(), shared_weights = (header vocab_size > 0).                 */
+typedef struct l2b_config {
+    int32_t dim;            /* transformer dimension                                       */
+    int32_t hidden_dim;     /* ffn hidden dimension                                        */
+    int32_t n_layers;
+    int32_t n_heads;
+    int32_t n_kv_heads;     /* < n_heads for multi-query / grouped-query (:291, :314-320)  */
+    int32_t vocab_size;
+    int32_t seq_len;
+    int32_t shared_weights; /* 1: classifier == token embedding table (:112)               */
+} l2b_config;
+
+/* Tensor-parallel placement of one context (BASELINE.json config 5).
+ * world_size == 1 means the whole model on `device`.  For world_size in {2,4,8}
+ * wq/wk/wv/w1/w3/wcls are split by output rows, wo/w2 by input columns, and the hidden
+ * vector is all-reduced after wo and after w2.  One process per rank: the caller moves
+ * `comm_id` (from l2b_comm_unique_id on rank 0) to every rank by its own means
+ * (bench.py uses torch.distributed).                                                      */
+typedef struct l2b_shard {
+    int32_t rank;
+    int32_t world_size;
+    int32_t device;          /* CUDA device ordinal for this context                        */
+    int32_t reserved;
+    uint8_t comm_id[128];    /* opaque rendezvous token; ignored when world_size == 1       */
+} l2b_shard;
+
+typedef struct l2b_ctx l2b_ctx;
+
+/* ---- lifecycle ---------------------------------------------------------------------- */
+
+/* Replaces Weights.init (src/main.zig:73-115) + RunState.init (:137-154) on the device.
+ *   host_weights : the checkpoint payload after the 28-byte header, exactly the `data`
+ *                  buffer of src/main.zig:955-967, laid out as :85-112; n_floats its length.
+ *   rope_cos/sin : optional (seq_len, head_size/2) tables the host computed with the
+ *                  expressions of :338-342 (so RoPE is bit-identical to the host's libm);
+ *                  NULL => the library computes them with the same expressions.
+ *   n_gpus       : must be 1 here; multi-GPU contexts are made with l2b_create_sharded.
+ * Supported shapes: dim % 4 == 0, hidden_dim % 4 == 0, head_size = dim/n_heads even and
+ * a multiple of 4, n_heads % n_kv_heads == 0.  Anything else => L2B_ERR_UNSUPPORTED.       */
+int32_t l2b_create(l2b_ctx **out, const l2b_config *cfg, const float *host_weights,
+                   uint64_t n_floats, const float *rope_cos, const float *rope_sin,
+                   int32_t n_gpus);
+
+/* Same, for one tensor-parallel rank.  host_weights is the FULL payload; the library
+ * uploads only this rank's slices.                                                         */
+int32_t l2b_create_sharded(l2b_ctx **out, const l2b_config *cfg, const float *host_weights,
+                           uint64_t n_floats, const float *rope_cos, const float *rope_sin,
+                           const l2b_shard *shard);
+
+/* Synthetic checkpoint of the given shape generated directly in device memory
+ * (stories110M / llama2-7B are not shipped; a 27 GB file is impractical).
+ * The generator is a counter-based integer hash, bit-identical to
+ * l2b_synth_fill_host() below, so a CPU checker can materialise the same weights.
+ * shard may be NULL (single GPU, device 0).                                                */
+int32_t l2b_create_synthetic(l2b_ctx **out, const l2b_config *cfg, uint64_t seed,
+                             const l2b_shard *shard);
+
+void l2b_destroy(l2b_ctx *ctx);
+
+/* Forget the KV cache (start a new generation at pos 0).  The reference runs one
+ * generation per process and has no such entry point; benches need it.                     */
+int32_t l2b_reset(l2b_ctx *ctx);
+
+/* ---- the hot path ------------------------------------------------------------------- */
+
+/* transformer(token, pos, ...) of src/main.zig:285-430.  On return host_logits[0..vocab)
+ * holds what the reference leaves in state.logits (:429); the caller may then mutate it
+ * exactly as :1002-1013 do.  pos must be 0 on the first call and may not skip ahead:
+ * pos <= (number of positions appended so far).  Synchronous.                               */
+int32_t l2b_forward(l2b_ctx *ctx, int32_t token, int32_t pos, float *host_logits);
+
+/* Same step, but the argmax of :715-726 (first maximum wins) runs on the device in the
+ * classifier epilogue and only the token id crosses PCIe.  The `-t 0` path (:1002-1003).   */
+int32_t l2b_forward_argmax(l2b_ctx *ctx, int32_t token, int32_t pos, int32_t *next);
+
+/* Zero-copy variant: runs the step and returns a pointer to the library's pinned host
+ * buffer of vocab_size logits (valid until the next call on this context).  A Zig host can
+ * point state.logits at it once and drop the copy.                                         */
+int32_t l2b_forward_pinned(l2b_ctx *ctx, int32_t token, int32_t pos, const float **logits);
+
+/* Whole temperature-0 generation loop of src/main.zig:995-1042 on the device: starts from
+ * `token` at position `pos`, runs up to n_steps steps, feeds forced[i] (if forced != NULL
+ * and forced[i] >= 0, like prompt forcing :999-1000) or the on-device argmax back in, and
+ * stops after emitting BOS (token 1, :1017-1019) when stop_on_bos != 0.  out_next[i] is the
+ * token chosen at step i; *n_done the number of transformer steps executed.                */
+int32_t l2b_generate_argmax(l2b_ctx *ctx, int32_t token, int32_t pos, int32_t n_steps,
+                            const int32_t *forced, int32_t stop_on_bos, int32_t *out_next,
+                            int32_t *n_done);
+
+/* ---- introspection ------------------------------------------------------------------- */
+
+const char *l2b_last_error(const l2b_ctx *ctx);     /* never NULL                           */
+const char *l2b_status_string(int32_t status);
+int32_t l2b_abi_version(void);
+
+/* Copies one RunState buffer (src/main.zig:119-135) of the last step to the host, for
+ * layer-level parity tests: 0=x 1=xb 2=hb 3=q 4=key_cache 5=value_cache 6=logits.
+ * Sharded contexts return this rank's slice.  n = capacity of dst in floats; *n_out the
+ * floats written.                                                                          */
+int32_t l2b_read_state(l2b_ctx *ctx, int32_t which, float *dst, uint64_t n, uint64_t *n_out);
+
+/* Device time (ms, CUDA events on the context's stream) of the last forward/generate call,
+ * and how many kernels of this library it launched.                                        */
+int32_t l2b_last_timing(const l2b_ctx *ctx, float *device_ms, int32_t *kernel_launches);
+
+/* Algorithmic bytes one step at position pos must read:
+ * weight bytes (this rank's shard) and KV-cache bytes.                                     */
+int32_t l2b_step_bytes(const l2b_ctx *ctx, int32_t pos, uint64_t *weight_bytes,
+                       uint64_t *kv_bytes);
+
+/* ---- multi-GPU rendezvous -------------------------------------------------------------- */
+int32_t l2b_comm_unique_id(uint8_t id[128]);
+
+/* ---- synthetic-weight generator, host mirror (for checkers) ---------------------------- */
+/* dst[j] = element (first + j) of a tensor with the given seed/distribution; identical to
+ * what l2b_create_synthetic puts on the device.                                            */
+void l2b_synth_fill_host(float *dst, uint64_t first, uint64_t count, uint64_t tensor_seed,
+                         double mean, double sigma, float lo, float hi);
+/* Whole payload in checkpoint order (src/main.zig:85-112).                                 */
+int32_t l2b_synth_checkpoint_host(const l2b_config *cfg, uint64_t seed, float *data,
+                                  uint64_t n_floats);
+uint64_t l2b_checkpoint_floats(const l2b_config *cfg);
+
+/* ---- single ops with HOST buffers (unit-test surface) ---------------------------------- */
+/* Each runs the same device code the hot path uses, on cuda:`device`, so the reference's
+ * own unit tests (src/main.zig:1078-1150) can be replayed against the GPU.                 */
+/* matmul (src/main.zig:485-498): xout(d) = W(d,n) . x(n)                                   */
+int32_t l2b_op_matmul(int32_t device, float *xout, const float *x, const float *w, int32_t d,
+                      int32_t n);
+/* rmsnorm (:432-468)                                                                       */
+int32_t l2b_op_rmsnorm(int32_t device, float *o, const float *x, const float *w, int32_t n);
+/* softmax (:687-706), in place                                                             */
+int32_t l2b_op_softmax(int32_t device, float *x, int32_t n);
+/* vector_weighted_sum_rows (:657-685)                                                      */
+int32_t l2b_op_weighted_sum_rows(int32_t device, float *xout, int32_t out_len, const float *rows,
+                                 int32_t row_stride, const float *weights, int32_t n_weights);
+/* One attention head over a KV cache slice (:361-389): q(head_size), keys/values are
+ * (n_pos, kv_stride) row-major with the head's slice starting at column 0.                 */
+int32_t l2b_op_attention_head(int32_t device, float *out, const float *q, const float *keys,
+                              const float *values, int32_t head_size, int32_t kv_stride,
+                              int32_t n_pos);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLAMA2_B200_H */

@@ -1,0 +1,14 @@
+"""Import alias for the package directory `llama2.zig_b200/` (a dot is not importable).
+
+    import llama2_zig_b200 as l2b
+"""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "llama2.zig_b200")
+_spec = importlib.util.spec_from_file_location(__name__, os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)
