@@ -145,6 +145,20 @@ int32_t l2b_read_state(l2b_ctx *ctx, int32_t which, float *dst, uint64_t n, uint
  * and how many kernels of this library it launched.                                        */
 int32_t l2b_last_timing(const l2b_ctx *ctx, float *device_ms, int32_t *kernel_launches);
 
+/* Per-kernel device times of ONE step (eager launches with a CUDA event between kernels, on
+ * the context's stream), for roofline accounting: `bytes` is the algorithmic traffic of that
+ * launch (weight rows x columns x 4, or the K and V rows attention reads).  The step is a
+ * real step (KV cache is appended, logits are produced).  out has room for cap entries;
+ * *n_out receives the number of kernels in a step.                                          */
+typedef struct l2b_kernel_time {
+    char name[24];          /* "qkv_rope", "attention", "wo", "w13_silu", "w2", "classifier" */
+    int32_t layer;          /* -1 for the classifier                                         */
+    float ms;
+    uint64_t bytes;
+} l2b_kernel_time;
+int32_t l2b_profile_step(l2b_ctx *ctx, int32_t token, int32_t pos, l2b_kernel_time *out,
+                         int32_t cap, int32_t *n_out);
+
 /* Algorithmic bytes one step at position pos must read:
  * weight bytes (this rank's shard) and KV-cache bytes.                                     */
 int32_t l2b_step_bytes(const l2b_ctx *ctx, int32_t pos, uint64_t *weight_bytes,

@@ -27,6 +27,10 @@ class L2BConfig(C.Structure):
                  "shared_weights")]
 
 
+class L2BKernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 24), ("layer", C.c_int32), ("ms", C.c_float), ("bytes", C.c_uint64)]
+
+
 class L2BShard(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world_size", C.c_int32), ("device", C.c_int32),
                 ("reserved", C.c_int32), ("comm_id", C.c_uint8 * 128)]
@@ -86,6 +90,7 @@ def load_library():
     lib.l2b_read_state.argtypes = [vp, C.c_int32, FP, C.c_uint64, U64P]
     lib.l2b_last_timing.argtypes = [vp, FP, IP]
     lib.l2b_step_bytes.argtypes = [vp, C.c_int32, U64P, U64P]
+    lib.l2b_profile_step.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(L2BKernelTime), C.c_int32, IP]
     lib.l2b_comm_unique_id.argtypes = [C.POINTER(C.c_uint8 * 128)]
     lib.l2b_synth_fill_host.argtypes = [FP, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double,
                                         C.c_double, C.c_float, C.c_float]
@@ -254,6 +259,14 @@ class Transformer:
         k = C.c_int32()
         _check(self.lib.l2b_last_timing(self.h, C.byref(ms), C.byref(k)), self.h)
         return ms.value, k.value
+
+    def profile_step(self, token, pos):
+        """Per-kernel (name, layer, ms, algorithmic bytes) of one real step (CUDA events)."""
+        cap = 8 * self.ck.n_layers + 8
+        arr = (L2BKernelTime * cap)()
+        n = C.c_int32()
+        _check(self.lib.l2b_profile_step(self.h, int(token), int(pos), arr, cap, C.byref(n)), self.h)
+        return [(arr[i].name.decode(), arr[i].layer, arr[i].ms, arr[i].bytes) for i in range(n.value)]
 
     def step_bytes(self, pos):
         w = C.c_uint64()

@@ -115,6 +115,10 @@ struct l2b_ctx {
     int last_launches = 0;
     std::string err;
     std::vector<void *> owned;              // device allocations to free
+    // per-kernel profiling (l2b_profile_step)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<l2b_kernel_time> prof_rec;
 };
 
 namespace {
@@ -271,7 +275,26 @@ int gemv_tpr(int n) {
     return tpr;
 }
 
-int launch_gemv(l2b_ctx *ctx, int epi, const GemvParams &p, cudaStream_t st) {
+int prof_mark(l2b_ctx *ctx, const char *name, int layer, uint64_t bytes, cudaStream_t st) {
+    if (!ctx->profiling) return L2B_OK;
+    cudaEvent_t ev;
+    L2B_CUDA(ctx, cudaEventCreate(&ev));
+    L2B_CUDA(ctx, cudaEventRecord(ev, st));
+    ctx->prof_ev.push_back(ev);
+    l2b_kernel_time r{};
+    snprintf(r.name, sizeof r.name, "%s", name);
+    r.layer = layer;
+    r.bytes = bytes;
+    ctx->prof_rec.push_back(r);
+    return L2B_OK;
+}
+
+int launch_gemv(l2b_ctx *ctx, int epi, const GemvParams &p, cudaStream_t st, const char *name = "gemv",
+                int layer = -1) {
+    {
+        int prc = prof_mark(ctx, name, layer, (uint64_t)p.total_rows * p.n * 4ull, st);
+        if (prc) return prc;
+    }
     const int tpr = gemv_tpr(p.n);
     gemv_fn fn = gemv_pick(epi, tpr);
     const size_t smem = (size_t)p.n * 4 * (1 + (p.delta ? 1 : 0) + (p.gamma ? 1 : 0));
@@ -297,6 +320,12 @@ int launch_gemv(l2b_ctx *ctx, int epi, const GemvParams &p, cudaStream_t st) {
 }
 
 int launch_attention(l2b_ctx *ctx, int layer, cudaStream_t st) {
+    if (ctx->profiling) {
+        int hpos = 0;   // the host knows pos only through the last set_ctl; stored in n_appended-1
+        hpos = ctx->n_appended > 0 ? ctx->n_appended - 1 : 0;
+        int prc = prof_mark(ctx, "attention", layer, 2ull * (uint64_t)(hpos + 1) * ctx->kv_loc * 4ull, st);
+        if (prc) return prc;
+    }
     AttnParams a{};
     a.ctl = ctx->ctl;
     a.q = ctx->q;
@@ -351,7 +380,7 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
         p.vcache = ctx->vcache + loff;
         p.rope_cos = ctx->rope_cos; p.rope_sin = ctx->rope_sin;
         p.head_size = ctx->head_size; p.kv_dim = ctx->kv_loc;
-        int rc = launch_gemv(ctx, EPI_QKV, p, st);
+        int rc = launch_gemv(ctx, EPI_QKV, p, st, "qkv_rope", l);
         if (rc) return rc;
 
         // ---- attention (:361-389)
@@ -366,7 +395,7 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
         o.w0 = ctx->wo + (size_t)l * dim * ctx->q_loc;
         o.total_rows = dim; o.rows0 = dim;
         o.out0 = ctx->delta_a;
-        rc = launch_gemv(ctx, EPI_STORE, o, st);
+        rc = launch_gemv(ctx, EPI_STORE, o, st, "wo", l);
         if (rc) return rc;
         if (ctx->world > 1)
             L2B_NCCL(ctx, g_nccl.AllReduce(ctx->delta_a, ctx->delta_a, dim, ncclFloat, ncclSum, ctx->comm, st));
@@ -385,7 +414,7 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
         f.rows0 = ctx->hid_loc;
         f.total_rows = 2 * ctx->hid_loc;
         f.out0 = ctx->hb;
-        rc = launch_gemv(ctx, EPI_SILU, f, st);
+        rc = launch_gemv(ctx, EPI_SILU, f, st, "w13_silu", l);
         if (rc) return rc;
 
         // ---- w2 (:419); residual (:422) deferred likewise
@@ -396,7 +425,7 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
         d.w0 = ctx->w2 + (size_t)l * dim * ctx->hid_loc;
         d.total_rows = dim; d.rows0 = dim;
         d.out0 = ctx->delta_f;
-        rc = launch_gemv(ctx, EPI_STORE, d, st);
+        rc = launch_gemv(ctx, EPI_STORE, d, st, "w2", l);
         if (rc) return rc;
         if (ctx->world > 1)
             L2B_NCCL(ctx, g_nccl.AllReduce(ctx->delta_f, ctx->delta_f, dim, ncclFloat, ncclSum, ctx->comm, st));
@@ -416,7 +445,7 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
     k.out0 = (ctx->world > 1) ? ctx->logits_loc : ctx->logits;
     k.amax = ctx->amax;
     k.row_base = ctx->rank * ctx->vocab_loc;
-    int rc = launch_gemv(ctx, want_argmax ? EPI_ARGMAX : EPI_STORE, k, st);
+    int rc = launch_gemv(ctx, want_argmax ? EPI_ARGMAX : EPI_STORE, k, st, "classifier", -1);
     if (rc) return rc;
     if (ctx->world > 1) {
         if (want_argmax)
@@ -892,6 +921,47 @@ int32_t l2b_last_timing(const l2b_ctx *ctx, float *device_ms, int32_t *kernel_la
     if (device_ms) *device_ms = ctx->last_ms;
     if (kernel_launches) *kernel_launches = ctx->last_launches;
     return L2B_OK;
+}
+
+int32_t l2b_profile_step(l2b_ctx *ctx, int32_t token, int32_t pos, l2b_kernel_time *out, int32_t cap,
+                         int32_t *n_out) {
+    int rc = check_step_args(ctx, token, pos);
+    if (rc) return rc;
+    if (!out || !n_out || cap <= 0) return fail(ctx, L2B_ERR_INVALID_ARG, "bad profile arguments");
+    L2B_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (pos + 1 > ctx->n_appended) ctx->n_appended = pos + 1;   // attention bytes use this
+    const int saved_appended = ctx->n_appended;
+    ctx->n_appended = pos + 1;
+    set_ctl_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, token, pos, 0, ctx->amax);
+    L2B_CUDA(ctx, cudaGetLastError());
+    ctx->profiling = true;
+    ctx->prof_ev.clear();
+    ctx->prof_rec.clear();
+    rc = enqueue_step(ctx, ctx->stream, false);
+    ctx->profiling = false;
+    ctx->n_appended = saved_appended;
+    cudaEvent_t last = nullptr;
+    if (rc == L2B_OK) {
+        if (cudaEventCreate(&last) != cudaSuccess || cudaEventRecord(last, ctx->stream) != cudaSuccess)
+            rc = fail(ctx, L2B_ERR_CUDA, "event record failed");
+    }
+    if (rc == L2B_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        rc = fail(ctx, L2B_ERR_CUDA, "profile step failed");
+    const int n = (int)ctx->prof_rec.size();
+    if (rc == L2B_OK) {
+        for (int i = 0; i < n; ++i) {
+            cudaEvent_t b = (i + 1 < n) ? ctx->prof_ev[i + 1] : last;
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, ctx->prof_ev[i], b);
+            ctx->prof_rec[i].ms = ms;
+            if (i < cap) out[i] = ctx->prof_rec[i];
+        }
+        *n_out = n;
+    }
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+    if (last) cudaEventDestroy(last);
+    ctx->prof_ev.clear();
+    return rc;
 }
 
 int32_t l2b_step_bytes(const l2b_ctx *ctx, int32_t pos, uint64_t *weight_bytes, uint64_t *kv_bytes) {
