@@ -199,6 +199,8 @@ def run_workload(workload, args, rank, world, dist, sync, flush, clock_index):
     from llama2_zig_b200.checkpoint import shape_checkpoint
 
     shape_key, positions, real = WORKLOADS[workload]
+    if args.positions:
+        positions = args.positions
     real_path = os.path.join(ROOT, "assets", "stories15M.bin")
     comm_id = None
     if world > 1:
@@ -324,6 +326,7 @@ def main():
     ap.add_argument("--workload", default="auto", choices=["auto"] + list(WORKLOADS))
     ap.add_argument("--also", default="auto", help="comma list of extra workloads reported under 'also' (N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--positions", type=int, default=0, help="override positions per step (profiling runs only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))

@@ -70,6 +70,15 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
         : "memory");
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-
+// serialization attribute may start while its predecessor is still running; everything before
+// pdl_wait() (barrier init, prefetch of immutable weights) overlaps the predecessor's tail.
+// pdl_wait() returns once the predecessor grid has completed and its writes are visible.
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------
 // Block-level reductions (warp shuffles + one smem hop).  Result returned to all threads.
 // scratch: >= NWARP + 1 floats of shared memory.
@@ -185,65 +194,24 @@ __device__ __forceinline__ const float *gemv_row_ptr(const GemvParams &p, int v)
     }
 }
 
-template <int TPR, int EPI>
-__global__ void __launch_bounds__(NT) gemv_kernel(const GemvParams p) {
-    constexpr int GROUPS = NT / TPR;           // row groups per CTA
-    constexpr int TILE_ROWS = GROUPS * GEMV_R;
-    constexpr int WPG = (TPR + 31) / 32;       // warps per group (TPR > 32)
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *xs = reinterpret_cast<float *>(smem_raw);   // n floats
-    float *aux = xs + p.n;                              // delta (n) then gamma (n) when fused
-    __shared__ uint64_t bar;
-    __shared__ float scratch[NWARP + 1];
-    __shared__ float red[NWARP][GEMV_R];
-    __shared__ unsigned long long blk_key;
-
+// ---- shared prologue: stage the activation vector (+ residual, + rmsnorm) into shared memory.
+// Must be called by all NT threads after pdl_wait(); thread 0 has already initialised `bar`.
+__device__ __forceinline__ void gemv_stage_input(const GemvParams &p, float *xs, float *aux,
+                                                 uint64_t *bar, float *scratch) {
     const int tid = threadIdx.x;
-    const int grp = tid / TPR, sub = tid % TPR;
     const int n4 = p.n >> 2;
-    const int ntiles = (p.total_rows + TILE_ROWS - 1) / TILE_ROWS;
-    const int nchunks = (n4 + TPR * GEMV_U - 1) / (TPR * GEMV_U);
-
-    if (p.ctl[CTL_DONE]) return;  // generation loop already ended (BOS)
-
-    // ---- issue the TMA staging of the activation vector
     const float *xsrc = p.emb ? p.emb + (size_t)p.ctl[CTL_TOKEN] * p.n : p.x_in;
     float *ds = aux;
     float *gs = p.delta ? aux + p.n : aux;
     if (tid == 0) {
-        mbar_init(&bar, 1);
-        mbar_fence_init();
         const uint32_t bytes = (uint32_t)p.n * 4u;
-        mbar_expect_tx(&bar, bytes * (1u + (p.delta ? 1u : 0u) + (p.gamma ? 1u : 0u)));
-        tma_load_1d(xs, xsrc, bytes, &bar);
-        if (p.delta) tma_load_1d(ds, p.delta, bytes, &bar);
-        if (p.gamma) tma_load_1d(gs, p.gamma, bytes, &bar);
+        mbar_expect_tx(bar, bytes * (1u + (p.delta ? 1u : 0u) + (p.gamma ? 1u : 0u)));
+        tma_load_1d(xs, xsrc, bytes, bar);
+        if (p.delta) tma_load_1d(ds, p.delta, bytes, bar);
+        if (p.gamma) tma_load_1d(gs, p.gamma, bytes, bar);
     }
-
-    // ---- first chunk of weights goes in flight before we wait for the activations
-    float4 wv[GEMV_R][GEMV_U];
-    int tile = blockIdx.x, chunk = 0;
-    auto issue = [&](int t, int ch) {
-        const int v0 = t * TILE_ROWS + grp * GEMV_R;
-#pragma unroll
-        for (int r = 0; r < GEMV_R; ++r) {
-            const int v = v0 + r;
-            const bool rok = v < p.total_rows;
-            const float4 *wr =
-                reinterpret_cast<const float4 *>(gemv_row_ptr<EPI>(p, rok ? v : 0));
-#pragma unroll
-            for (int u = 0; u < GEMV_U; ++u) {
-                const int c = (ch * GEMV_U + u) * TPR + sub;
-                wv[r][u] = (rok && c < n4) ? ldg_stream(wr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-    };
-    if (tile < ntiles) issue(tile, 0);
-
-    // ---- wait for the staged vector, optional residual add + rmsnorm in shared memory
     __syncthreads();  // barrier init visible to all waiters
-    mbar_wait(&bar, 0);
+    mbar_wait(bar, 0);
     if (p.delta || p.gamma || p.x_out) {
         float4 *xs4 = reinterpret_cast<float4 *>(xs);
         const float4 *ds4 = reinterpret_cast<const float4 *>(ds);
@@ -277,6 +245,113 @@ __global__ void __launch_bounds__(NT) gemv_kernel(const GemvParams p) {
         }
         __syncthreads();
     }
+}
+
+// ---- shared epilogue for one adjacent pair of virtual rows (v0 even)
+template <int EPI>
+__device__ __forceinline__ void gemv_epilogue_pair(const GemvParams &p, int v0, float a0, float a1,
+                                                   int pos, unsigned long long &best) {
+    if (v0 >= p.total_rows) return;
+    if (EPI == EPI_STORE || EPI == EPI_ARGMAX) {
+        p.out0[v0] = a0;
+        if (v0 + 1 < p.total_rows) p.out0[v0 + 1] = a1;
+        if (EPI == EPI_ARGMAX) {
+            const unsigned long long k0 = argmax_key(a0, p.row_base + v0);
+            best = k0 > best ? k0 : best;
+            if (v0 + 1 < p.total_rows) {
+                const unsigned long long k1 = argmax_key(a1, p.row_base + v0 + 1);
+                best = k1 > best ? k1 : best;
+            }
+        }
+    } else if (EPI == EPI_QKV) {
+        // rows (v0, v0+1) are an adjacent pair of q, k or v (segment sizes are even)
+        if (v0 < p.rows0 + p.rows1) {
+            const bool is_q = v0 < p.rows0;
+            const int i = is_q ? v0 : v0 - p.rows0;       // index within q / k
+            const int pr = (i % p.head_size) >> 1;          // :338 (i % head_size)
+            const float fcr = p.rope_cos[(size_t)pos * (p.head_size >> 1) + pr];
+            const float fci = p.rope_sin[(size_t)pos * (p.head_size >> 1) + pr];
+            // :348-349, evaluated without FMA contraction like the reference
+            const float r0 = __fsub_rn(__fmul_rn(a0, fcr), __fmul_rn(a1, fci));
+            const float r1 = __fadd_rn(__fmul_rn(a0, fci), __fmul_rn(a1, fcr));
+            float *dst = is_q ? p.out0 + i : p.kcache + (size_t)pos * p.kv_dim + i;   // :355,:357
+            *reinterpret_cast<float2 *>(dst) = make_float2(r0, r1);
+        } else {
+            const int i = v0 - p.rows0 - p.rows1;
+            *reinterpret_cast<float2 *>(p.vcache + (size_t)pos * p.kv_dim + i) = make_float2(a0, a1);  // :356,:358
+        }
+    } else {  // EPI_SILU
+        const float sg = __fmul_rn(a0, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-a0))));   // :412
+        p.out0[v0 >> 1] = __fmul_rn(sg, a1);                                          // :416
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void gemv_finish_argmax(const GemvParams &p, unsigned long long best,
+                                                   unsigned long long *blk_key) {
+    if (EPI != EPI_ARGMAX) return;
+    // CTA-level max, then one 64-bit atomicMax per CTA
+    if (threadIdx.x == 0) *blk_key = 0ull;
+    __syncthreads();
+    if (best) atomicMax(blk_key, best);
+    __syncthreads();
+    if (threadIdx.x == 0 && *blk_key) atomicMax(p.amax, *blk_key);
+}
+
+// ---- v1: small / latency-bound shapes.  TPR threads per pair of rows, tiles strided over CTAs.
+template <int TPR, int EPI>
+__global__ void __launch_bounds__(NT) gemv_kernel(const GemvParams p) {
+    constexpr int GROUPS = NT / TPR;           // row groups per CTA
+    constexpr int TILE_ROWS = GROUPS * GEMV_R;
+    constexpr int WPG = (TPR + 31) / 32;       // warps per group (TPR > 32)
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *xs = reinterpret_cast<float *>(smem_raw);   // n floats
+    float *aux = xs + p.n;                              // delta (n) then gamma (n) when fused
+    __shared__ uint64_t bar;
+    __shared__ float scratch[NWARP + 1];
+    __shared__ float red[NWARP][GEMV_R];
+    __shared__ unsigned long long blk_key;
+
+    const int tid = threadIdx.x;
+    const int grp = tid / TPR, sub = tid % TPR;
+    const int n4 = p.n >> 2;
+    const int ntiles = (p.total_rows + TILE_ROWS - 1) / TILE_ROWS;
+    const int nchunks = (n4 + TPR * GEMV_U - 1) / (TPR * GEMV_U);
+
+    // ---- first chunk of weights goes in flight before anything that depends on earlier kernels
+    float4 wv[GEMV_R][GEMV_U];
+    int tile = blockIdx.x, chunk = 0;
+    auto issue = [&](int t, int ch) {
+        const int v0 = t * TILE_ROWS + grp * GEMV_R;
+#pragma unroll
+        for (int r = 0; r < GEMV_R; ++r) {
+            const int v = v0 + r;
+            const bool rok = v < p.total_rows;
+            const float4 *wr =
+                reinterpret_cast<const float4 *>(gemv_row_ptr<EPI>(p, rok ? v : 0));
+#pragma unroll
+            for (int u = 0; u < GEMV_U; ++u) {
+                const int c = (ch * GEMV_U + u) * TPR + sub;
+                wv[r][u] = (rok && c < n4) ? ldg_stream(wr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    };
+    if (tile < ntiles) issue(tile, 0);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    bool triggered = false;
+    if (tile + (int)gridDim.x >= ntiles && nchunks == 1) {   // this CTA is already on its last chunk
+        pdl_launch_dependents();
+        triggered = true;
+    }
+
+    // ---- everything below reads what earlier kernels of this step wrote
+    pdl_wait();
+    if (p.ctl[CTL_DONE]) return;  // generation loop already ended (BOS)
+    gemv_stage_input(p, xs, aux, &bar, scratch);
 
     const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
     const int pos = p.ctl[CTL_POS];
@@ -299,7 +374,13 @@ __global__ void __launch_bounds__(NT) gemv_kernel(const GemvParams p) {
         // ---- put the next chunk in flight
         int ntile = tile, nchunk = chunk + 1;
         if (nchunk == nchunks) { ntile = tile + gridDim.x; nchunk = 0; }
-        if (ntile < ntiles) issue(ntile, nchunk);
+        if (ntile < ntiles) {
+            issue(ntile, nchunk);
+        }
+        if (!triggered && (ntile >= ntiles || (ntile + (int)gridDim.x >= ntiles && nchunk == nchunks - 1))) {
+            pdl_launch_dependents();   // our last chunk is in flight: let the successor start prefetching
+            triggered = true;
+        }
 
         if (chunk == nchunks - 1) {
             // ---- reduce the GEMV_R partial dot products across the TPR threads of the group
@@ -329,59 +410,399 @@ __global__ void __launch_bounds__(NT) gemv_kernel(const GemvParams p) {
                     }
                 }
             }
-            // ---- epilogue, one thread per group
-            const int v0 = tile * TILE_ROWS + grp * GEMV_R;
-            if (sub == 0 && v0 < p.total_rows) {
-                if (EPI == EPI_STORE || EPI == EPI_ARGMAX) {
-                    p.out0[v0] = acc[0];
-                    if (v0 + 1 < p.total_rows) p.out0[v0 + 1] = acc[1];
-                    if (EPI == EPI_ARGMAX) {
-                        unsigned long long k0 = argmax_key(acc[0], p.row_base + v0);
-                        best = k0 > best ? k0 : best;
-                        if (v0 + 1 < p.total_rows) {
-                            unsigned long long k1 = argmax_key(acc[1], p.row_base + v0 + 1);
-                            best = k1 > best ? k1 : best;
-                        }
-                    }
-                } else if (EPI == EPI_QKV) {
-                    // rows (v0, v0+1) are an adjacent pair of q, k or v (segment sizes are even)
-                    if (v0 < p.rows0 + p.rows1) {
-                        const bool is_q = v0 < p.rows0;
-                        const int i = is_q ? v0 : v0 - p.rows0;       // index within q / k
-                        const int pr = (i % p.head_size) >> 1;          // :338 (i % head_size)
-                        const float fcr = p.rope_cos[(size_t)pos * (p.head_size >> 1) + pr];
-                        const float fci = p.rope_sin[(size_t)pos * (p.head_size >> 1) + pr];
-                        const float a = acc[0], b = acc[1];
-                        // :348-349, evaluated without FMA contraction like the reference
-                        const float r0 = __fsub_rn(__fmul_rn(a, fcr), __fmul_rn(b, fci));
-                        const float r1 = __fadd_rn(__fmul_rn(a, fci), __fmul_rn(b, fcr));
-                        float *dst = is_q ? p.out0 + i : p.kcache + (size_t)pos * p.kv_dim + i; // :355,:357
-                        *reinterpret_cast<float2 *>(dst) = make_float2(r0, r1);
-                    } else {
-                        const int i = v0 - p.rows0 - p.rows1;
-                        *reinterpret_cast<float2 *>(p.vcache + (size_t)pos * p.kv_dim + i) =
-                            make_float2(acc[0], acc[1]);                                     // :356,:358
-                    }
-                } else {  // EPI_SILU
-                    const float h = acc[0];
-                    const float sg = __fmul_rn(h, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-h))));  // :412
-                    p.out0[v0 >> 1] = __fmul_rn(sg, acc[1]);                                    // :416
-                }
-            }
+            if (sub == 0)
+                gemv_epilogue_pair<EPI>(p, tile * TILE_ROWS + grp * GEMV_R, acc[0], acc[1], pos, best);
 #pragma unroll
             for (int r = 0; r < GEMV_R; ++r) acc[r] = 0.0f;
         }
         tile = ntile;
         chunk = nchunk;
     }
+    if (!triggered) pdl_launch_dependents();
+    gemv_finish_argmax<EPI>(p, best, &blk_key);
+}
 
-    if (EPI == EPI_ARGMAX) {
-        // CTA-level max, then one 64-bit atomicMax per CTA
-        if (tid == 0) blk_key = 0ull;
+// ---- v2: bandwidth-bound shapes (n >= 1024, many MB).  The whole CTA (256 threads) walks the
+// columns of GEMV8_R = 8 rows at once: per column step one LDS.128 of x is shared by eight
+// LDG.128 of weights (32 FMAs), two steps are kept in flight per thread (16 x 128-bit loads),
+// and the cross-thread reduction happens once per 8 rows with a transposing butterfly
+// (9 shuffles for 8 rows instead of 40) and one barrier.  Each CTA owns a CONTIGUOUS, balanced
+// range of row pairs (+-1 pair), so all CTAs stream the same number of bytes and finish together.
+constexpr int GEMV8_R = 8;
+
+template <int EPI>
+__global__ void __launch_bounds__(NT, 2) gemv8_kernel(const GemvParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *xs = reinterpret_cast<float *>(smem_raw);
+    float *aux = xs + p.n;
+    __shared__ uint64_t bar;
+    __shared__ float scratch[NWARP + 1];
+    __shared__ float red[2][NWARP][GEMV8_R];
+    __shared__ unsigned long long blk_key;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n4 = p.n >> 2;
+    const int nsteps = (n4 + NT - 1) / NT;             // column steps per tile
+    // balanced contiguous ranges of row pairs
+    const int npairs = (p.total_rows + 1) >> 1;
+    const int base = npairs / (int)gridDim.x, rem = npairs % (int)gridDim.x;
+    const int b = blockIdx.x;
+    const int pair0 = b * base + min(b, rem);
+    const int pair1 = pair0 + base + (b < rem ? 1 : 0);
+    const int r0 = pair0 * 2, r1 = min(pair1 * 2, p.total_rows);
+    const int ntiles = (r1 - r0 + GEMV8_R - 1) / GEMV8_R;
+    const int total = ntiles * nsteps;                 // flattened (tile, step) space
+
+    float4 wa[GEMV8_R], wb[GEMV8_R];
+    auto issue = [&](float4 (&w)[GEMV8_R], int it) {
+        const int t = it / nsteps, st = it - t * nsteps;
+        const int c = st * NT + tid;
+        const int v0 = r0 + t * GEMV8_R;
+#pragma unroll
+        for (int r = 0; r < GEMV8_R; ++r) {
+            const int v = v0 + r;
+            const bool ok = (v < r1) && (c < n4);
+            const float4 *wr = reinterpret_cast<const float4 *>(gemv_row_ptr<EPI>(p, ok ? v : 0));
+            w[r] = ok ? ldg_stream(wr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    if (0 < total) issue(wa, 0);
+    if (1 < total) issue(wb, 1);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    bool triggered = false;
+    if (total <= 2) { pdl_launch_dependents(); triggered = true; }
+
+    pdl_wait();
+    if (p.ctl[CTL_DONE]) return;
+    gemv_stage_input(p, xs, aux, &bar, scratch);
+
+    const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
+    const int pos = p.ctl[CTL_POS];
+    unsigned long long best = 0ull;
+    float acc[GEMV8_R];
+#pragma unroll
+    for (int r = 0; r < GEMV8_R; ++r) acc[r] = 0.0f;
+
+    auto consume = [&](const float4 (&w)[GEMV8_R], int it) {
+        const int t = it / nsteps, st = it - t * nsteps;
+        const int c = st * NT + tid;
+        if (c < n4) {
+            const float4 xv = xs4[c];
+#pragma unroll
+            for (int r = 0; r < GEMV8_R; ++r) acc[r] = dot4(w[r], xv, acc[r]);
+        }
+        if (st != nsteps - 1) return;
+        // ---- end of a tile: transposing butterfly, lane L (L % 4 == 0) ends with row L / 4
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = (lane & 16) ? acc[i] : acc[i + 4];
+            const float keep = (lane & 16) ? acc[i + 4] : acc[i];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = (lane & 8) ? acc[i] : acc[i + 2];
+            const float keep = (lane & 8) ? acc[i + 2] : acc[i];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {
+            const float send = (lane & 4) ? acc[0] : acc[1];
+            const float keep = (lane & 4) ? acc[1] : acc[0];
+            acc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 2);
+        acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+        const int par = t & 1;                         // double-buffered: one barrier per tile
+        if ((lane & 3) == 0) red[par][warp][lane >> 2] = acc[0];
         __syncthreads();
-        if (best) atomicMax(&blk_key, best);
+        if (tid < GEMV8_R / 2) {
+            float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+            for (int w8 = 0; w8 < NWARP; ++w8) {       // fixed order
+                s0 += red[par][w8][2 * tid];
+                s1 += red[par][w8][2 * tid + 1];
+            }
+            const int v0 = r0 + t * GEMV8_R + 2 * tid;
+            if (v0 < r1) gemv_epilogue_pair<EPI>(p, v0, s0, s1, pos, best);
+        }
+#pragma unroll
+        for (int r = 0; r < GEMV8_R; ++r) acc[r] = 0.0f;
+    };
+
+    for (int it = 0; it < total; it += 2) {
+        consume(wa, it);
+        if (it + 2 < total) issue(wa, it + 2);
+        if (it + 1 < total) {
+            consume(wb, it + 1);
+            if (it + 3 < total) issue(wb, it + 3);
+        }
+        if (!triggered && it + 4 >= total) {           // the last loads are in flight
+            pdl_launch_dependents();
+            triggered = true;
+        }
+    }
+    if (!triggered) pdl_launch_dependents();
+    gemv_finish_argmax<EPI>(p, best, &blk_key);
+}
+
+// ---- v3: TMA-fed streaming GEMV for bandwidth-bound shapes.
+//
+// Measured on this B200 (profiles/microbench/read_bw.cu): a pure read stream needs ~128 KB in
+// flight per SM; register-fed LDG loops only get there with >= 1024 resident threads per SM,
+// while a shared-memory ring filled by cp.async.bulk reaches 7.2 TB/s with one small CTA.  So:
+// one persistent CTA per SM; a producer thread streams 32 KB stages (8 rows x 256 float4, one
+// 4 KB bulk copy per row) of this CTA's contiguous row range into an NSTAGE ring, starting
+// BEFORE griddepcontrol.wait (weights are immutable), so the ring is already full when the
+// previous kernel finishes; 8 consumer warps read each stage with conflict-free LDS.128, share
+// one LDS.128 of x across the 8 rows, and reduce once per 8 rows (transposing butterfly).
+constexpr int TMA_NSTAGE = 5;
+constexpr int TMA_STAGE_FLOATS = GEMV8_R * NT * 4;        // 8 rows x 256 float4 = 32 KB
+constexpr int TMA_THREADS = NT + 64;                       // 8 consumer warps + producer warp + epilogue warp
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp roles: warps 0-7 consume stages (LDS.128 + FMA, butterfly reduce per 8 rows), warp 8 lane 0
+// produces (TMA), warp 9 runs the epilogues (RoPE / KV append / SiLU / argmax) off the consumers'
+// critical path: consumers hand it the 8x8 per-warp partial sums through a double-buffered
+// shared array guarded by two mbarrier pairs, so no block-wide barrier exists in the main loop.
+template <int EPI>
+__global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const GemvParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *ring = reinterpret_cast<float *>(smem_raw);                 // NSTAGE x 32 KB
+    float *xs = ring + (size_t)TMA_NSTAGE * TMA_STAGE_FLOATS;          // n floats
+    float *aux = xs + p.n;                                             // delta, gamma
+    __shared__ uint64_t full[TMA_NSTAGE], empty[TMA_NSTAGE], xbar, tile_full[2], tile_free[2];
+    __shared__ float scratch[NWARP + 2];
+    __shared__ float red[2][NWARP][GEMV8_R];
+    __shared__ float rope_s[2][128];                                   // cos/sin row of `pos` (head_size/2 <= 128)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n4 = p.n >> 2;
+    const int nsteps = (n4 + NT - 1) / NT;
+    const int npairs = (p.total_rows + 1) >> 1;
+    const int base = npairs / (int)gridDim.x, rem = npairs % (int)gridDim.x;
+    const int b = blockIdx.x;
+    const int pair0 = b * base + min(b, rem);
+    const int pair1 = pair0 + base + (b < rem ? 1 : 0);
+    const int r0 = pair0 * 2, r1 = min(pair1 * 2, p.total_rows);
+    const int ntiles = (r1 - r0 + GEMV8_R - 1) / GEMV8_R;
+    const int total = ntiles * nsteps;
+
+    if (tid == 0) {
+        for (int s = 0; s < TMA_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWARP); }
+        mbar_init(&xbar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&tile_full[s], NWARP); mbar_init(&tile_free[s], 1); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // ---- producer state (warp 8): lane r issues row r's bulk copy, lane 0 owns the barriers.
+    // The ring is filled before waiting on the previous kernel (weights are immutable).
+    int p_it = 0, p_stage = 0, p_tile = 0, p_step = 0;
+    uint32_t p_phase = 0;
+    const float *p_row = nullptr;                                      // this lane's row in the current tile
+    auto produce_one = [&]() {                                         // executed by all 32 lanes of warp 8
+        const int c0 = p_step * NT;                                    // first float4 column
+        const int cols4 = min(NT, n4 - c0);
+        const int v0 = r0 + p_tile * GEMV8_R;
+        const int rows = min(GEMV8_R, r1 - v0);
+        if (p_step == 0 && lane < rows) p_row = gemv_row_ptr<EPI>(p, v0 + lane);
+        if (lane == 0) {
+            mbar_wait(&empty[p_stage], p_phase ^ 1);
+            mbar_expect_tx(&full[p_stage], (uint32_t)(rows * cols4 * 16));
+        }
+        __syncwarp();
+        if (lane < rows)
+            tma_load_1d(ring + (size_t)p_stage * TMA_STAGE_FLOATS + lane * NT * 4, p_row + (size_t)c0 * 4,
+                        (uint32_t)(cols4 * 16), &full[p_stage]);
+        ++p_it;
+        if (++p_step == nsteps) { p_step = 0; ++p_tile; }
+        if (++p_stage == TMA_NSTAGE) { p_stage = 0; p_phase ^= 1; }
+    };
+    if (warp == NWARP) {
+        while (p_it < total && p_it < TMA_NSTAGE) produce_one();
+        if (p_it >= total) pdl_launch_dependents();
+    }
+
+    // ---- everything below reads what earlier kernels of this step wrote
+    pdl_wait();
+    if (p.ctl[CTL_DONE]) {
+        // generation already ended: drain the bulk copies already aimed at our shared memory
+        if (tid == 0)
+            for (int s = 0; s < TMA_NSTAGE && s < total; ++s) mbar_wait(&full[s], 0);
         __syncthreads();
-        if (tid == 0 && blk_key) atomicMax(p.amax, blk_key);
+        return;
+    }
+    const int pos = p.ctl[CTL_POS];
+
+    // stage the activation vector (all threads take part in the barriers of this phase)
+    {
+        const float *xsrc = p.emb ? p.emb + (size_t)p.ctl[CTL_TOKEN] * p.n : p.x_in;
+        float *ds = aux;
+        float *gs = p.delta ? aux + p.n : aux;
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)p.n * 4u;
+            mbar_expect_tx(&xbar, bytes * (1u + (p.delta ? 1u : 0u) + (p.gamma ? 1u : 0u)));
+            tma_load_1d(xs, xsrc, bytes, &xbar);
+            if (p.delta) tma_load_1d(ds, p.delta, bytes, &xbar);
+            if (p.gamma) tma_load_1d(gs, p.gamma, bytes, &xbar);
+        }
+        if (EPI == EPI_QKV && tid >= NT + 32) {          // epilogue warp: this position's RoPE row
+            const int half = p.head_size >> 1;
+            for (int i = lane; i < half; i += 32) {
+                rope_s[0][i] = p.rope_cos[(size_t)pos * half + i];
+                rope_s[1][i] = p.rope_sin[(size_t)pos * half + i];
+            }
+        }
+        mbar_wait(&xbar, 0);
+        if (p.delta || p.gamma || p.x_out) {
+            float4 *xs4w = reinterpret_cast<float4 *>(xs);
+            const float4 *ds4 = reinterpret_cast<const float4 *>(ds);
+            float ssq = 0.0f;
+            for (int i = tid; i < n4; i += TMA_THREADS) {
+                float4 v = xs4w[i];
+                if (p.delta) {
+                    const float4 d = ds4[i];
+                    v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;   // accum(), :708-713
+                    xs4w[i] = v;
+                }
+                if (p.x_out && blockIdx.x == 0) reinterpret_cast<float4 *>(p.x_out)[i] = v;
+                ssq = fmaf(v.x, v.x, ssq); ssq = fmaf(v.y, v.y, ssq);
+                ssq = fmaf(v.z, v.z, ssq); ssq = fmaf(v.w, v.w, ssq);
+            }
+            if (p.gamma) {
+                ssq = warp_sum(ssq);
+                if (lane == 0) scratch[warp] = ssq;
+                __syncthreads();
+                float ss = (lane < NWARP + 2) ? scratch[lane] : 0.0f;
+                ss = warp_sum(ss);
+                ss /= (float)p.n;            // :452
+                ss += 1e-5f;                 // :453
+                const float sc = 1.0f / sqrtf(ss);  // :454
+                const float4 *gs4 = reinterpret_cast<const float4 *>(gs);
+                for (int i = tid; i < n4; i += TMA_THREADS) {
+                    float4 v = xs4w[i];
+                    const float4 g = gs4[i];
+                    v.x = __fmul_rn(__fmul_rn(v.x, sc), g.x);   // (x*s)*w, :462
+                    v.y = __fmul_rn(__fmul_rn(v.y, sc), g.y);
+                    v.z = __fmul_rn(__fmul_rn(v.z, sc), g.z);
+                    v.w = __fmul_rn(__fmul_rn(v.w, sc), g.w);
+                    xs4w[i] = v;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    if (warp == NWARP) {
+        // ---- producer warp: keep the ring full
+        while (p_it < total) {
+            produce_one();
+            if (p_it == total) pdl_launch_dependents();   // last stage in flight
+        }
+        return;
+    }
+
+    if (warp == NWARP + 1) {
+        // ---- epilogue warp: lanes 0..3 own the four row pairs of each tile
+        unsigned long long best = 0ull;
+        for (int t = 0; t < ntiles; ++t) {
+            const int par = t & 1, use = t >> 1;
+            mbar_wait(&tile_full[par], use & 1);
+            float s0 = 0.0f, s1 = 0.0f;
+            if (lane < GEMV8_R / 2) {
+#pragma unroll
+                for (int w8 = 0; w8 < NWARP; ++w8) {       // fixed order
+                    s0 += red[par][w8][2 * lane];
+                    s1 += red[par][w8][2 * lane + 1];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tile_free[par]);  // consumers may overwrite red[par]
+            const int vp = r0 + t * GEMV8_R + 2 * lane;
+            if (lane < GEMV8_R / 2 && vp < r1) {
+                if (EPI == EPI_QKV && vp < p.rows0 + p.rows1) {
+                    const bool is_q = vp < p.rows0;
+                    const int i = is_q ? vp : vp - p.rows0;
+                    const int pr = (i % p.head_size) >> 1;                                  // :338
+                    const float fcr = rope_s[0][pr], fci = rope_s[1][pr];
+                    const float q0 = __fsub_rn(__fmul_rn(s0, fcr), __fmul_rn(s1, fci));      // :348
+                    const float q1 = __fadd_rn(__fmul_rn(s0, fci), __fmul_rn(s1, fcr));      // :349
+                    float *dst = is_q ? p.out0 + i : p.kcache + (size_t)pos * p.kv_dim + i;  // :355,:357
+                    *reinterpret_cast<float2 *>(dst) = make_float2(q0, q1);
+                } else {
+                    gemv_epilogue_pair<EPI>(p, vp, s0, s1, pos, best);
+                }
+            }
+        }
+        if (EPI == EPI_ARGMAX) {
+#pragma unroll
+            for (int o = 2; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+                best = other > best ? other : best;
+            }
+            if (lane == 0 && best) atomicMax(p.amax, best);
+        }
+        return;
+    }
+
+    // ---- consumers (warps 0..7)
+    const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
+    float acc[GEMV8_R];
+#pragma unroll
+    for (int r = 0; r < GEMV8_R; ++r) acc[r] = 0.0f;
+    int c_stage = 0;
+    uint32_t c_phase = 0;
+    int t = 0, st = 0;
+    for (int it = 0; it < total; ++it, ++st) {
+        if (st == nsteps) { st = 0; ++t; }
+        const int c = st * NT + tid;
+        const int v0 = r0 + t * GEMV8_R;
+        const int rows = min(GEMV8_R, r1 - v0);
+        mbar_wait(&full[c_stage], c_phase);
+        if (c < n4) {
+            const float4 *w4 = reinterpret_cast<const float4 *>(ring + (size_t)c_stage * TMA_STAGE_FLOATS) + tid;
+            const float4 xv = xs4[c];
+#pragma unroll
+            for (int r = 0; r < GEMV8_R; ++r)
+                if (r < rows) acc[r] = dot4(w4[r * NT], xv, acc[r]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[c_stage]);      // this warp is done with the stage
+        if (++c_stage == TMA_NSTAGE) { c_stage = 0; c_phase ^= 1; }
+        if (st != nsteps - 1) continue;
+        // ---- end of a tile: transposing butterfly, lane L (L % 4 == 0) ends with row L / 4
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = (lane & 16) ? acc[i] : acc[i + 4];
+            const float keep = (lane & 16) ? acc[i + 4] : acc[i];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = (lane & 8) ? acc[i] : acc[i + 2];
+            const float keep = (lane & 8) ? acc[i + 2] : acc[i];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {
+            const float send = (lane & 4) ? acc[0] : acc[1];
+            const float keep = (lane & 4) ? acc[1] : acc[0];
+            acc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 2);
+        acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+        const int par = t & 1, use = t >> 1;
+        mbar_wait(&tile_free[par], (use & 1) ^ 1);        // epilogue warp has read use-1 of red[par]
+        if ((lane & 3) == 0) red[par][warp][lane >> 2] = acc[0];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tile_full[par]);
+#pragma unroll
+        for (int r = 0; r < GEMV8_R; ++r) acc[r] = 0.0f;
     }
 }
 
@@ -427,8 +848,8 @@ __device__ __forceinline__ int attn_lanes_per_row(int hs4) {
     return (hs4 % 8 == 0) ? 8 : (hs4 % 4 == 0) ? 4 : (hs4 % 2 == 0) ? 2 : 1;
 }
 
-// scores for positions [t0,t1) of one head into sc[0..t1-t0)
-__device__ __forceinline__ void attn_scores(float *sc, const float *qs, const float *kbase,
+// scores for positions [t0,t1) of one head into sc[0..t1-t0); q fragments live in registers
+__device__ __forceinline__ void attn_scores(float *sc, const float *qg, const float *kbase,
                                             int kv_dim, int head_size, int t0, int t1) {
     const int hs4 = head_size >> 2;
     const int lpr = attn_lanes_per_row(hs4);
@@ -436,7 +857,7 @@ __device__ __forceinline__ void attn_scores(float *sc, const float *qs, const fl
     const int rows_per_warp = 32 / lpr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lr = lane % lpr, rw = lane / lpr;
-    const float4 *q4 = reinterpret_cast<const float4 *>(qs);
+    const float4 *q4 = reinterpret_cast<const float4 *>(qg);
     const float root_hs = sqrtf((float)head_size);
     for (int tb = t0 + warp * rows_per_warp; tb < t1; tb += NWARP * rows_per_warp) {
         const int t = tb + rw;
@@ -445,7 +866,7 @@ __device__ __forceinline__ void attn_scores(float *sc, const float *qs, const fl
             const float4 *k4 = reinterpret_cast<const float4 *>(kbase + (size_t)t * kv_dim);
             for (int f = 0; f < nf; ++f) {
                 const int j = lr + f * lpr;
-                acc = dot4(__ldg(k4 + j), q4[j], acc);
+                acc = dot4(__ldg(k4 + j), __ldg(q4 + j), acc);
             }
         }
         for (int o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -453,16 +874,15 @@ __device__ __forceinline__ void attn_scores(float *sc, const float *qs, const fl
     }
 }
 
-// out[0..head_size) (+)= sum_t w[t-t0] * V[t]; result left in red[0..head_size) (shared).
-// red must hold (NT / (head_size/4)) * head_size floats.
+// red[g][0..head_size) = sum over this group's rows of w[t-t0] * V[t]   (G = NT / (head_size/4))
 __device__ __forceinline__ void attn_weighted_rows(float *red, const float *w, const float *vbase,
                                                    int kv_dim, int head_size, int t0, int t1) {
     const int hs4 = head_size >> 2;
     const int G = NT / hs4;
     const int tid = threadIdx.x;
     const int g = tid / hs4, c = tid % hs4;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     if (g < G) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int t = t0 + g; t < t1; t += G) {
             const float wt = w[t - t0];
             const float4 v = __ldg(reinterpret_cast<const float4 *>(vbase + (size_t)t * kv_dim) + c);
@@ -471,20 +891,13 @@ __device__ __forceinline__ void attn_weighted_rows(float *red, const float *w, c
         }
         reinterpret_cast<float4 *>(red)[g * hs4 + c] = a;
     }
-    __syncthreads();
-    // fold the G partial vectors in fixed order (thread i only touches column i: no hazard)
-    if (tid < head_size) {
-        float s = 0.0f;
-        for (int gg = 0; gg < G; ++gg) s += red[gg * head_size + tid];
-        red[tid] = s;
-    }
-    __syncthreads();
 }
 
 __global__ void __launch_bounds__(NT) attention_kernel(const AttnParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ float scratch[NWARP + 1];
     __shared__ int is_last;
+    pdl_launch_dependents();
+    pdl_wait();
     if (p.ctl[CTL_DONE]) return;
 
     const int h = blockIdx.x, s = blockIdx.y;
@@ -498,47 +911,44 @@ __global__ void __launch_bounds__(NT) attention_kernel(const AttnParams p) {
     const int t1 = min(T, t0 + chunk);
     const int len = t1 - t0;
 
-    // shared layout: q[hs] | red[G*hs] | sc[chunk_cap]
+    // shared layout: red[G*hs] | sc[chunk_cap]
     const int hs4 = hs >> 2;
     const int G = NT / hs4;
-    float *qs = reinterpret_cast<float *>(smem_raw);
-    float *red = qs + hs;
+    float *red = reinterpret_cast<float *>(smem_raw);
     float *sc = red + G * hs;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const size_t hoff = (size_t)(h / p.kv_mul) * hs;   // :369, :382
-    for (int i = tid; i < hs; i += NT) qs[i] = p.q[(size_t)h * hs + i];
+
+    attn_scores(sc, p.q + (size_t)h * hs, p.kcache + hoff, p.kv_dim, hs, t0, t1);
     __syncthreads();
 
-    attn_scores(sc, qs, p.kcache + hoff, p.kv_dim, hs, t0, t1);
-    __syncthreads();
-
-    // softmax pieces over this split (:690-705)
+    // softmax pieces (:690-705).  Every warp recomputes max and sum over the whole split from
+    // shared memory (identical order in every warp), which costs a few shuffles instead of
+    // four block-wide barriers.
     float m = -INFINITY;
-    for (int i = tid; i < len; i += NT) m = fmaxf(m, sc[i]);
-    m = block_max(m, scratch);
-    float l = 0.0f;
-    for (int i = tid; i < len; i += NT) {
-        const float e = expf(sc[i] - m);
-        sc[i] = e;
-        l += e;
-    }
-    l = block_sum(l, scratch);
-    if (active == 1) {
-        for (int i = tid; i < len; i += NT) sc[i] = sc[i] / l;   // :703-705
-    }
+    for (int i = lane; i < len; i += 32) m = fmaxf(m, sc[i]);
+    m = warp_max(m);
+    for (int i = tid; i < len; i += NT) sc[i] = expf(sc[i] - m);   // :699
     __syncthreads();
+    float l = 0.0f;
+    for (int i = lane; i < len; i += 32) l += sc[i];
+    l = warp_sum(l);
 
     attn_weighted_rows(red, sc, p.vcache + hoff, p.kv_dim, hs, t0, t1);
+    __syncthreads();
+    float o = 0.0f;
+    if (tid < hs) {
+        for (int gg = 0; gg < G; ++gg) o += red[gg * hs + tid];   // fixed order
+    }
 
     if (active == 1) {
-        if (tid < hs) p.xb[(size_t)h * hs + tid] = red[tid];
+        if (tid < hs) p.xb[(size_t)h * hs + tid] = o / l;        // normalisation of :703-705
         return;
     }
 
     // ---- publish the partial, last arriver merges
-    float *po = p.part_o + ((size_t)h * p.nsplit + s) * hs;
-    if (tid < hs) po[tid] = red[tid];
+    if (tid < hs) p.part_o[((size_t)h * p.nsplit + s) * hs + tid] = o;
     if (tid == 0) {
         p.part_ml[((size_t)h * p.nsplit + s) * 2 + 0] = m;
         p.part_ml[((size_t)h * p.nsplit + s) * 2 + 1] = l;
@@ -560,9 +970,9 @@ __global__ void __launch_bounds__(NT) attention_kernel(const AttnParams p) {
     for (int j = 0; j < active; ++j) Lsum += expf(ml[j * 2] - M) * ml[j * 2 + 1];
     if (tid < hs) {
         const volatile float *pb = p.part_o + (size_t)h * p.nsplit * hs;
-        float o = 0.0f;
-        for (int j = 0; j < active; ++j) o = fmaf(expf(ml[j * 2] - M), pb[(size_t)j * hs + tid], o);
-        p.xb[(size_t)h * hs + tid] = o / Lsum;
+        float acc = 0.0f;
+        for (int j = 0; j < active; ++j) acc = fmaf(expf(ml[j * 2] - M), pb[(size_t)j * hs + tid], acc);
+        p.xb[(size_t)h * hs + tid] = acc / Lsum;
     }
 }
 

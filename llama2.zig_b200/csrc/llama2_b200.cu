@@ -106,6 +106,9 @@ struct l2b_ctx {
     cudaGraphExec_t graph_logits = nullptr, graph_argmax = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool use_graphs = true;
+    bool use_pdl = true;
+    bool big_kernel_tma = true;              // bandwidth-bound GEMVs: TMA-ring kernel (false: register-fed 8-row kernel)
+    long long gemv8_min_bytes = 8ll << 20;   // >= this many weight bytes (and n >= 1024): 8-row kernel; -1 = never
     int launches_per_step = 0;
     // comm
     ncclComm_t comm = nullptr;
@@ -267,6 +270,7 @@ gemv_fn gemv_pick(int epi, int tpr) {
 }
 
 constexpr int kMaxDynSmem = 200 * 1024;
+constexpr int kMaxSmemOptin = 227 * 1024 - 2048;   // static __shared__ of the kernels stays under 2 KB
 
 int gemv_tpr(int n) {
     const int n4 = n / 4;
@@ -289,32 +293,72 @@ int prof_mark(l2b_ctx *ctx, const char *name, int layer, uint64_t bytes, cudaStr
     return L2B_OK;
 }
 
+gemv_fn gemv_tma_pick(int epi) {
+    switch (epi) {
+    case EPI_STORE: return gemv_tma_kernel<EPI_STORE>;
+    case EPI_ARGMAX: return gemv_tma_kernel<EPI_ARGMAX>;
+    case EPI_QKV: return gemv_tma_kernel<EPI_QKV>;
+    default: return gemv_tma_kernel<EPI_SILU>;
+    }
+}
+
+gemv_fn gemv8_pick(int epi) {
+    switch (epi) {
+    case EPI_STORE: return gemv8_kernel<EPI_STORE>;
+    case EPI_ARGMAX: return gemv8_kernel<EPI_ARGMAX>;
+    case EPI_QKV: return gemv8_kernel<EPI_QKV>;
+    default: return gemv8_kernel<EPI_SILU>;
+    }
+}
+
 int launch_gemv(l2b_ctx *ctx, int epi, const GemvParams &p, cudaStream_t st, const char *name = "gemv",
                 int layer = -1) {
     {
         int prc = prof_mark(ctx, name, layer, (uint64_t)p.total_rows * p.n * 4ull, st);
         if (prc) return prc;
     }
+    const size_t xbytes = (size_t)p.n * 4 * (1 + (p.delta ? 1 : 0) + (p.gamma ? 1 : 0));
+    // bandwidth-bound shapes take the TMA-ring kernel (or the register-fed 8-row kernel when
+    // L2B_GEMV_BIG=ldg), latency-bound ones the fine-grained kernel
+    const bool big = ctx->gemv8_min_bytes >= 0 && p.n >= 1024 &&
+                     (uint64_t)p.total_rows * p.n * 4ull >= (uint64_t)ctx->gemv8_min_bytes;
+    const size_t ring = (size_t)TMA_NSTAGE * TMA_STAGE_FLOATS * 4;
+    const bool tma = big && ctx->big_kernel_tma && ring + xbytes <= (size_t)kMaxSmemOptin && p.head_size <= 256;
+    const size_t smem = tma ? ring + xbytes : xbytes;
+    if (smem > (size_t)kMaxSmemOptin) return fail(ctx, L2B_ERR_UNSUPPORTED, "activation vector too large for shared memory");
     const int tpr = gemv_tpr(p.n);
-    gemv_fn fn = gemv_pick(epi, tpr);
-    const size_t smem = (size_t)p.n * 4 * (1 + (p.delta ? 1 : 0) + (p.gamma ? 1 : 0));
-    if (smem > (size_t)kMaxDynSmem) return fail(ctx, L2B_ERR_UNSUPPORTED, "activation vector too large for shared memory");
-    static bool attr_done[4][6][16] = {};
-    const int ti = tpr == 8 ? 0 : tpr == 16 ? 1 : tpr == 32 ? 2 : tpr == 64 ? 3 : tpr == 128 ? 4 : 5;
+    gemv_fn fn = tma ? gemv_tma_pick(epi) : big ? gemv8_pick(epi) : gemv_pick(epi, tpr);
+    static bool attr_done[4][8][16] = {};
+    const int ti = tma ? 7 : big ? 6 : tpr == 8 ? 0 : tpr == 16 ? 1 : tpr == 32 ? 2 : tpr == 64 ? 3 : tpr == 128 ? 4 : 5;
     if (!attr_done[epi][ti][ctx->device & 15]) {
-        L2B_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        L2B_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
         attr_done[epi][ti][ctx->device & 15] = true;
     }
+    const int threads = tma ? TMA_THREADS : NT;
     int occ = 0;
-    L2B_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, NT, smem));
+    L2B_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem));
     if (occ < 1) occ = 1;
-    const int tile_rows = (NT / tpr) * GEMV_R;
-    const int ntiles = (p.total_rows + tile_rows - 1) / tile_rows;
     int grid = ctx->num_sms * occ;
-    if (grid > ntiles) grid = ntiles;
+    if (big) {
+        const int npairs = (p.total_rows + 1) / 2;
+        if (grid > npairs) grid = npairs;
+    } else {
+        const int tile_rows = (NT / tpr) * GEMV_R;
+        const int ntiles = (p.total_rows + tile_rows - 1) / tile_rows;
+        if (grid > ntiles) grid = ntiles;
+    }
     if (grid < 1) grid = 1;
-    fn<<<grid, NT, smem, st>>>(p);
-    L2B_CUDA(ctx, cudaGetLastError());
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(threads);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = ctx->use_pdl ? 1 : 0;
+    L2B_CUDA(ctx, cudaLaunchKernelEx(&lc, fn, p));
     ++ctx->last_launches;
     return L2B_OK;
 }
@@ -341,9 +385,17 @@ int launch_attention(l2b_ctx *ctx, int layer, cudaStream_t st) {
     a.kv_mul = ctx->kv_mul;
     a.nsplit = ctx->nsplit;
     a.min_chunk = ctx->min_chunk;
-    dim3 grid(ctx->heads_loc, ctx->nsplit);
-    attention_kernel<<<grid, NT, ctx->attn_smem, st>>>(a);
-    L2B_CUDA(ctx, cudaGetLastError());
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(ctx->heads_loc, ctx->nsplit);
+    lc.blockDim = dim3(NT);
+    lc.dynamicSmemBytes = ctx->attn_smem;
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = ctx->use_pdl ? 1 : 0;
+    L2B_CUDA(ctx, cudaLaunchKernelEx(&lc, attention_kernel, a));
     ++ctx->last_launches;
     return L2B_OK;
 }
@@ -626,7 +678,7 @@ int common_create(l2b_ctx **out, const l2b_config *cfg, const Source &src, uint6
         int cap = (int)((S + ns - 1) / ns);
         if (cap < ctx->min_chunk) cap = ctx->min_chunk;
         const int G = NT / (int)(hs / 4);
-        ctx->attn_smem = (int)((hs + (uint64_t)G * hs + cap) * sizeof(float));
+        ctx->attn_smem = (int)(((uint64_t)G * hs + cap) * sizeof(float));
         if (ctx->attn_smem > kMaxDynSmem) {
             ctx->err = "seq_len too large for the attention kernel's shared memory";
             g_create_error = ctx->err;
@@ -684,6 +736,12 @@ int common_create(l2b_ctx **out, const l2b_config *cfg, const Source &src, uint6
     {
         const char *env = getenv("L2B_NO_GRAPH");
         ctx->use_graphs = !(env && env[0] == '1');
+        const char *env2 = getenv("L2B_NO_PDL");
+        ctx->use_pdl = !(env2 && env2[0] == '1');
+        const char *env3 = getenv("L2B_GEMV8_MIN_BYTES");
+        if (env3) ctx->gemv8_min_bytes = atoll(env3);
+        const char *env4 = getenv("L2B_GEMV_BIG");
+        if (env4 && strcmp(env4, "ldg") == 0) ctx->big_kernel_tma = false;
     }
     // one eager step of each flavour: sets function attributes outside capture and surfaces
     // launch errors before a graph hides them (it scribbles on KV row 0, rewritten by step 0)
@@ -1138,7 +1196,7 @@ int32_t l2b_op_attention_head(int32_t device, float *out, const float *q, const 
     int cap = (n_pos + nsplit - 1) / nsplit;
     if (cap < 64) cap = 64;
     const int G = NT / (head_size / 4);
-    const size_t smem = ((size_t)head_size + (size_t)G * head_size + cap) * sizeof(float);
+    const size_t smem = ((size_t)G * head_size + cap) * sizeof(float);
     if (smem > (size_t)kMaxDynSmem) { g_create_error = "n_pos too large"; return L2B_ERR_UNSUPPORTED; }
     cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     attention_kernel<<<dim3(1, nsplit), NT, smem>>>(a);

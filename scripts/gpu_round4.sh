@@ -1,0 +1,15 @@
+#!/bin/bash
+TAG=${1:-r01d}
+OUT=gpurun_out
+mkdir -p $OUT
+timeout 1200 python -m pytest tests -q -m gpu -x > $OUT/pytest_gpu_$TAG.log 2>&1
+tail -3 $OUT/pytest_gpu_$TAG.log
+for mode in tma ldg; do
+  L2B_GEMV_BIG=$mode timeout 900 python bench.py --workload llama2-7B --also none --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench_${TAG}_$mode.json 2> $OUT/bench_${TAG}_$mode.err
+  tail -c 300 $OUT/bench_${TAG}_$mode.err
+done
+L2B_GEMV8_MIN_BYTES=-1 timeout 900 python bench.py --workload llama2-7B --also none --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench_${TAG}_v1.json 2> $OUT/bench_${TAG}_v1.err
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemv_tma_kernel' \
+    -s 2000 -c 8 -f -o $OUT/prof_7b_$TAG python bench.py --workload llama2-7B --positions 4 --steps 1 --warmup 3 \
+    --also none --no-cpu-baseline > $OUT/ncu_7b_$TAG.log 2>&1
+tail -2 $OUT/ncu_7b_$TAG.log

@@ -58,7 +58,10 @@ def test_softmax(l2b):
 
 
 @pytest.mark.parametrize("d,n", [(1, 4), (2, 12), (3, 3), (7, 5), (16, 288), (64, 768), (33, 2048),
-                                 (10, 4096), (6, 11008), (1000, 300), (5, 36), (2, 1028)])
+                                 (10, 4096), (6, 11008), (1000, 300), (5, 36), (2, 1028),
+                                 # >= 8 MB and n >= 1024: the 8-row bandwidth kernel (odd rows, odd
+                                 # column-step counts, ragged last tile)
+                                 (1000, 4096), (3001, 1024), (513, 11008), (2052, 1028)])
 def test_matmul_vs_oracle(l2b, oracle, d, n):
     rng = np.random.default_rng(d * 100003 + n)
     x = rng.standard_normal(n).astype(np.float32)

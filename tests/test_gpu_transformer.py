@@ -201,5 +201,5 @@ def test_determinism_and_reset(l2b, stories15m):
         for a, b in zip(run1, run2):
             assert np.array_equal(a, b)
         w, kv = t.step_bytes(0)
-        assert w == 60_766_848 + 4 * 288        # SURVEY.md 8d weight bytes + the embedding row
+        assert w == 60_766_848                  # SURVEY.md 8d weight bytes per token
         assert kv == 4 * 6 * 2 * 288
