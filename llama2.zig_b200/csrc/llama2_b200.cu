@@ -852,9 +852,12 @@ void l2b_destroy(l2b_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
+    // graphs first: NCCL keeps a communicator alive (ncclCommDestroy spins) while captured
+    // graphs still reference it
     if (ctx->graph_logits) cudaGraphExecDestroy(ctx->graph_logits);
     if (ctx->graph_argmax) cudaGraphExecDestroy(ctx->graph_argmax);
+    cudaDeviceSynchronize();
+    if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
     for (void *p : ctx->owned) cudaFree(p);
     if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
     if (ctx->h_ints) cudaFreeHost(ctx->h_ints);
