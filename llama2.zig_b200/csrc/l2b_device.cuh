@@ -79,6 +79,17 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// System-scope signalling for the fused tensor-parallel all-reduce over NVLink peer memory.
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_sys_add(unsigned int *p, unsigned int v) {
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+constexpr int MAX_TP = 8;
+
 // ---------------------------------------------------------------------------------------
 // Block-level reductions (warp shuffles + one smem hop).  Result returned to all threads.
 // scratch: >= NWARP + 1 floats of shared memory.
@@ -133,9 +144,10 @@ __device__ __forceinline__ unsigned long long argmax_key(float v, int idx) {
 // ---------------------------------------------------------------------------------------
 // Step control block (device memory, 8 ints):
 //   [0] token  [1] pos  [2] done flag (generation loop saw BOS)  [3] step index in generate
-//   [4] stop-on-BOS enabled
+//   [4] stop-on-BOS enabled  [5] epoch: number of decode steps started on this context (never reset;
+//       the tensor-parallel exchange counters are compared against epoch * CTAs-per-producer)
 // ---------------------------------------------------------------------------------------
-enum { CTL_TOKEN = 0, CTL_POS = 1, CTL_DONE = 2, CTL_STEP = 3, CTL_STOP_ON_BOS = 4, CTL_WORDS = 8 };
+enum { CTL_TOKEN = 0, CTL_POS = 1, CTL_DONE = 2, CTL_STEP = 3, CTL_STOP_ON_BOS = 4, CTL_EPOCH = 5, CTL_WORDS = 8 };
 
 // ---------------------------------------------------------------------------------------
 // GEMV: out = W(rows, n) . xs(n), W row-major fp32 (src/main.zig:485-498, :530-605).
@@ -154,7 +166,8 @@ enum GemvEpi {
     EPI_STORE = 0,   // out[v] = acc                                   (wo, w2, wcls; :392,:419,:429)
     EPI_ARGMAX = 1,  // EPI_STORE + device argmax                       (:715-726 fused, 8f.1)
     EPI_QKV = 2,     // RoPE on (even,odd) pairs + KV-cache append     (:308-358)
-    EPI_SILU = 3     // hb[i] = silu(w1.x) * (w3.x)                     (:405-416)
+    EPI_SILU = 3,    // hb[i] = silu(w1.x) * (w3.x)                     (:405-416)
+    EPI_XCHG = 4     // tensor parallel: partial rows stored into every rank's exchange buffer (8e)
 };
 
 struct GemvParams {
@@ -177,6 +190,19 @@ struct GemvParams {
     int head_size, kv_dim;
     unsigned long long *amax;  // ARGMAX: packed running maximum (must be 0 before the launch)
     int row_base;              // ARGMAX: global index of out row 0 (vocab shard offset)
+    int nstage;                // gemv_tma_kernel: ring depth (2..TMA_MAX_STAGES)
+    // ---- tensor-parallel exchange (fused GEMV + all-reduce over peer memory); unused when xworld == 0
+    // producer side (EPI_XCHG): every rank's landing area for MY partial rows of this reduce point,
+    // and the counter there that my CTAs bump (system-scope release) when their rows have landed
+    float *xout_peer[MAX_TP];
+    unsigned int *xflag_peer[MAX_TP];
+    // consumer side: my landing areas (xworld x n floats, one per source rank) and counters of the
+    // reduce point whose sum is this kernel's pending residual; a source rank is complete when its
+    // counter reaches epoch * xcount_per_step (xcount_per_step = row pairs of the reduce point)
+    const float *xparts;
+    const unsigned int *xflags;
+    int xworld, xcount_per_step;
+    int bump_epoch;            // set on the first kernel of a step: CTA 0 increments ctl[CTL_EPOCH]
 };
 
 template <int EPI>
@@ -210,8 +236,28 @@ __device__ __forceinline__ void gemv_stage_input(const GemvParams &p, float *xs,
         if (p.delta) tma_load_1d(ds, p.delta, bytes, bar);
         if (p.gamma) tma_load_1d(gs, p.gamma, bytes, bar);
     }
-    __syncthreads();  // barrier init visible to all waiters
+    if (p.xparts) {
+        // fused all-reduce, consumer half: wait until every rank's partial rows have landed here
+        if (tid < p.xworld) {
+            const unsigned int want = (unsigned int)p.ctl[CTL_EPOCH] * (unsigned int)p.xcount_per_step;
+            while ((int)(ld_acquire_sys(p.xflags + tid) - want) < 0) { }
+        }
+    }
+    __syncthreads();  // barrier init visible to all waiters; exchange data visible to all threads
     mbar_wait(bar, 0);
+    if (p.xparts) {
+        float4 *xs4 = reinterpret_cast<float4 *>(xs);
+        const float4 *pp = reinterpret_cast<const float4 *>(p.xparts);
+        for (int i = tid; i < n4; i += NT) {
+            float4 v = xs4[i];
+            for (int r = 0; r < p.xworld; ++r) {          // fixed rank order: every rank gets the same x
+                const float4 d = __ldcg(pp + (size_t)r * n4 + i);
+                v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
+            }
+            xs4[i] = v;
+        }
+        __syncthreads();
+    }
     if (p.delta || p.gamma || p.x_out) {
         float4 *xs4 = reinterpret_cast<float4 *>(xs);
         const float4 *ds4 = reinterpret_cast<const float4 *>(ds);
@@ -252,7 +298,13 @@ template <int EPI>
 __device__ __forceinline__ void gemv_epilogue_pair(const GemvParams &p, int v0, float a0, float a1,
                                                    int pos, unsigned long long &best) {
     if (v0 >= p.total_rows) return;
-    if (EPI == EPI_STORE || EPI == EPI_ARGMAX) {
+    if (EPI == EPI_XCHG) {
+        // my partial of rows (v0, v0+1) goes to every rank (incl. me) over NVLink: posted stores
+        for (int r = 0; r < p.xworld; ++r) {
+            if (v0 + 1 < p.total_rows) *reinterpret_cast<float2 *>(p.xout_peer[r] + v0) = make_float2(a0, a1);
+            else p.xout_peer[r][v0] = a0;
+        }
+    } else if (EPI == EPI_STORE || EPI == EPI_ARGMAX) {
         p.out0[v0] = a0;
         if (v0 + 1 < p.total_rows) p.out0[v0 + 1] = a1;
         if (EPI == EPI_ARGMAX) {
@@ -296,6 +348,19 @@ __device__ __forceinline__ void gemv_finish_argmax(const GemvParams &p, unsigned
     if (best) atomicMax(blk_key, best);
     __syncthreads();
     if (threadIdx.x == 0 && *blk_key) atomicMax(p.amax, *blk_key);
+}
+
+// Producer half of the fused all-reduce for the block-structured kernels: every thread that stored
+// partial rows fences at system scope, then one thread per destination rank bumps that rank's
+// counter for (reduce point, this rank).
+// The counters count ROW PAIRS landed (not CTAs), so one step always adds ceil(rows/2) per
+// (reduce point, source rank) whichever kernel flavour or grid size produced them.
+template <int EPI>
+__device__ __forceinline__ void gemv_finish_xchg(const GemvParams &p, unsigned int my_pairs) {
+    if (EPI != EPI_XCHG) return;
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < p.xworld && my_pairs) red_release_sys_add(p.xflag_peer[threadIdx.x], my_pairs);
 }
 
 // ---- v1: small / latency-bound shapes.  TPR threads per pair of rows, tiles strided over CTAs.
@@ -351,6 +416,7 @@ __global__ void __launch_bounds__(NT) gemv_kernel(const GemvParams p) {
     // ---- everything below reads what earlier kernels of this step wrote
     pdl_wait();
     if (p.ctl[CTL_DONE]) return;  // generation loop already ended (BOS)
+    if (p.bump_epoch && blockIdx.x == 0 && tid == 0) const_cast<int *>(p.ctl)[CTL_EPOCH] += 1;
     gemv_stage_input(p, xs, aux, &bar, scratch);
 
     const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
@@ -420,6 +486,13 @@ __global__ void __launch_bounds__(NT) gemv_kernel(const GemvParams p) {
     }
     if (!triggered) pdl_launch_dependents();
     gemv_finish_argmax<EPI>(p, best, &blk_key);
+    if (EPI == EPI_XCHG) {
+        const int npairs_all = (p.total_rows + 1) >> 1;
+        unsigned int mine = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+            mine += (unsigned int)max(0, min(GROUPS, npairs_all - t * GROUPS));
+        gemv_finish_xchg<EPI>(p, mine);
+    }
 }
 
 // ---- v2: bandwidth-bound shapes (n >= 1024, many MB).  The whole CTA (256 threads) walks the
@@ -477,6 +550,7 @@ __global__ void __launch_bounds__(NT, 2) gemv8_kernel(const GemvParams p) {
 
     pdl_wait();
     if (p.ctl[CTL_DONE]) return;
+    if (p.bump_epoch && blockIdx.x == 0 && tid == 0) const_cast<int *>(p.ctl)[CTL_EPOCH] += 1;
     gemv_stage_input(p, xs, aux, &bar, scratch);
 
     const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
@@ -546,6 +620,7 @@ __global__ void __launch_bounds__(NT, 2) gemv8_kernel(const GemvParams p) {
     }
     if (!triggered) pdl_launch_dependents();
     gemv_finish_argmax<EPI>(p, best, &blk_key);
+    gemv_finish_xchg<EPI>(p, (unsigned int)(pair1 - pair0));
 }
 
 // ---- v3: TMA-fed streaming GEMV for bandwidth-bound shapes.
@@ -558,7 +633,7 @@ __global__ void __launch_bounds__(NT, 2) gemv8_kernel(const GemvParams p) {
 // BEFORE griddepcontrol.wait (weights are immutable), so the ring is already full when the
 // previous kernel finishes; 8 consumer warps read each stage with conflict-free LDS.128, share
 // one LDS.128 of x across the 8 rows, and reduce once per 8 rows (transposing butterfly).
-constexpr int TMA_NSTAGE = 5;
+constexpr int TMA_MAX_STAGES = 6;                         // ring depth is a launch parameter (GemvParams::nstage)
 constexpr int TMA_STAGE_FLOATS = GEMV8_R * NT * 4;        // 8 rows x 256 float4 = 32 KB
 constexpr int TMA_THREADS = NT + 64;                       // 8 consumer warps + producer warp + epilogue warp
 
@@ -571,12 +646,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // critical path: consumers hand it the 8x8 per-warp partial sums through a double-buffered
 // shared array guarded by two mbarrier pairs, so no block-wide barrier exists in the main loop.
 template <int EPI>
-__global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const GemvParams p) {
+__global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NSTAGE = p.nstage;
     float *ring = reinterpret_cast<float *>(smem_raw);                 // NSTAGE x 32 KB
-    float *xs = ring + (size_t)TMA_NSTAGE * TMA_STAGE_FLOATS;          // n floats
-    float *aux = xs + p.n;                                             // delta, gamma
-    __shared__ uint64_t full[TMA_NSTAGE], empty[TMA_NSTAGE], xbar, tile_full[2], tile_free[2];
+    float *xs = ring + (size_t)NSTAGE * TMA_STAGE_FLOATS;              // n floats
+    __shared__ uint64_t full[TMA_MAX_STAGES], empty[TMA_MAX_STAGES], xbar, tile_full[2], tile_free[2];
     __shared__ float scratch[NWARP + 2];
     __shared__ float red[2][NWARP][GEMV8_R];
     __shared__ float rope_s[2][128];                                   // cos/sin row of `pos` (head_size/2 <= 128)
@@ -594,7 +669,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const GemvPara
     const int total = ntiles * nsteps;
 
     if (tid == 0) {
-        for (int s = 0; s < TMA_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWARP); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWARP); }
         mbar_init(&xbar, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&tile_full[s], NWARP); mbar_init(&tile_free[s], 1); }
         mbar_fence_init();
@@ -622,10 +697,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const GemvPara
                         (uint32_t)(cols4 * 16), &full[p_stage]);
         ++p_it;
         if (++p_step == nsteps) { p_step = 0; ++p_tile; }
-        if (++p_stage == TMA_NSTAGE) { p_stage = 0; p_phase ^= 1; }
+        if (++p_stage == NSTAGE) { p_stage = 0; p_phase ^= 1; }
     };
     if (warp == NWARP) {
-        while (p_it < total && p_it < TMA_NSTAGE) produce_one();
+        while (p_it < total && p_it < NSTAGE) produce_one();
         if (p_it >= total) pdl_launch_dependents();
     }
 
@@ -634,23 +709,23 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const GemvPara
     if (p.ctl[CTL_DONE]) {
         // generation already ended: drain the bulk copies already aimed at our shared memory
         if (tid == 0)
-            for (int s = 0; s < TMA_NSTAGE && s < total; ++s) mbar_wait(&full[s], 0);
+            for (int s = 0; s < NSTAGE && s < total; ++s) mbar_wait(&full[s], 0);
         __syncthreads();
         return;
     }
     const int pos = p.ctl[CTL_POS];
+    if (p.bump_epoch && blockIdx.x == 0 && tid == 0) const_cast<int *>(p.ctl)[CTL_EPOCH] += 1;
 
-    // stage the activation vector (all threads take part in the barriers of this phase)
+    // stage the activation vector (all threads take part in the barriers of this phase).  Only x
+    // goes through shared memory; the pending residual and the rmsnorm gain are read once,
+    // straight from L2, which keeps the CTA's footprint small enough for the NEXT kernel's CTA
+    // to be co-resident and pre-fill its ring while this one is still streaming.
     {
         const float *xsrc = p.emb ? p.emb + (size_t)p.ctl[CTL_TOKEN] * p.n : p.x_in;
-        float *ds = aux;
-        float *gs = p.delta ? aux + p.n : aux;
         if (tid == 0) {
             const uint32_t bytes = (uint32_t)p.n * 4u;
-            mbar_expect_tx(&xbar, bytes * (1u + (p.delta ? 1u : 0u) + (p.gamma ? 1u : 0u)));
+            mbar_expect_tx(&xbar, bytes);
             tma_load_1d(xs, xsrc, bytes, &xbar);
-            if (p.delta) tma_load_1d(ds, p.delta, bytes, &xbar);
-            if (p.gamma) tma_load_1d(gs, p.gamma, bytes, &xbar);
         }
         if (EPI == EPI_QKV && tid >= NT + 32) {          // epilogue warp: this position's RoPE row
             const int half = p.head_size >> 1;
@@ -659,23 +734,64 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const GemvPara
                 rope_s[1][i] = p.rope_sin[(size_t)pos * half + i];
             }
         }
-        mbar_wait(&xbar, 0);
-        if (p.delta || p.gamma || p.x_out) {
-            float4 *xs4w = reinterpret_cast<float4 *>(xs);
-            const float4 *ds4 = reinterpret_cast<const float4 *>(ds);
-            float ssq = 0.0f;
-            for (int i = tid; i < n4; i += TMA_THREADS) {
-                float4 v = xs4w[i];
-                if (p.delta) {
-                    const float4 d = ds4[i];
-                    v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;   // accum(), :708-713
-                    xs4w[i] = v;
+        // each thread owns the float4 columns tid, tid + 320, ...; fetch its residual slice now
+        constexpr int MAXV = 4;                           // n <= 4 * 320 * 4 = 5120 floats when fused
+        float4 dv[MAXV];
+        const float4 *d4 = reinterpret_cast<const float4 *>(p.delta);
+        const bool have_delta = p.delta || p.xparts;
+        if (p.xparts) {
+            // fused all-reduce, consumer half: wait for every rank's partial rows, sum in rank order
+            if (tid < p.xworld) {
+                const unsigned int want = (unsigned int)p.ctl[CTL_EPOCH] * (unsigned int)p.xcount_per_step;
+                while ((int)(ld_acquire_sys(p.xflags + tid) - want) < 0) { }
+            }
+            __syncthreads();
+            const float4 *pp = reinterpret_cast<const float4 *>(p.xparts);
+#pragma unroll
+            for (int k = 0; k < MAXV; ++k) {
+                const int i = tid + k * TMA_THREADS;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < n4) {
+                    for (int r = 0; r < p.xworld; ++r) {
+                        const float4 d = __ldcg(pp + (size_t)r * n4 + i);
+                        a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w;
+                    }
                 }
-                if (p.x_out && blockIdx.x == 0) reinterpret_cast<float4 *>(p.x_out)[i] = v;
-                ssq = fmaf(v.x, v.x, ssq); ssq = fmaf(v.y, v.y, ssq);
-                ssq = fmaf(v.z, v.z, ssq); ssq = fmaf(v.w, v.w, ssq);
+                dv[k] = a;
+            }
+        } else if (p.delta) {
+#pragma unroll
+            for (int k = 0; k < MAXV; ++k) {
+                const int i = tid + k * TMA_THREADS;
+                dv[k] = (i < n4) ? __ldcg(d4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        mbar_wait(&xbar, 0);
+        if (have_delta || p.gamma || p.x_out) {
+            float4 *xs4w = reinterpret_cast<float4 *>(xs);
+            float ssq = 0.0f;
+#pragma unroll
+            for (int k = 0; k < MAXV; ++k) {
+                const int i = tid + k * TMA_THREADS;
+                if (i < n4) {
+                    float4 v = xs4w[i];
+                    if (have_delta) {
+                        v.x += dv[k].x; v.y += dv[k].y; v.z += dv[k].z; v.w += dv[k].w;   // accum(), :708-713
+                        xs4w[i] = v;
+                    }
+                    if (p.x_out && blockIdx.x == 0) reinterpret_cast<float4 *>(p.x_out)[i] = v;
+                    ssq = fmaf(v.x, v.x, ssq); ssq = fmaf(v.y, v.y, ssq);
+                    ssq = fmaf(v.z, v.z, ssq); ssq = fmaf(v.w, v.w, ssq);
+                }
             }
             if (p.gamma) {
+                const float4 *g4 = reinterpret_cast<const float4 *>(p.gamma);
+                float4 gv[MAXV];
+#pragma unroll
+                for (int k = 0; k < MAXV; ++k) {
+                    const int i = tid + k * TMA_THREADS;
+                    gv[k] = (i < n4) ? __ldg(g4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 ssq = warp_sum(ssq);
                 if (lane == 0) scratch[warp] = ssq;
                 __syncthreads();
@@ -684,15 +800,17 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const GemvPara
                 ss /= (float)p.n;            // :452
                 ss += 1e-5f;                 // :453
                 const float sc = 1.0f / sqrtf(ss);  // :454
-                const float4 *gs4 = reinterpret_cast<const float4 *>(gs);
-                for (int i = tid; i < n4; i += TMA_THREADS) {
-                    float4 v = xs4w[i];
-                    const float4 g = gs4[i];
-                    v.x = __fmul_rn(__fmul_rn(v.x, sc), g.x);   // (x*s)*w, :462
-                    v.y = __fmul_rn(__fmul_rn(v.y, sc), g.y);
-                    v.z = __fmul_rn(__fmul_rn(v.z, sc), g.z);
-                    v.w = __fmul_rn(__fmul_rn(v.w, sc), g.w);
-                    xs4w[i] = v;
+#pragma unroll
+                for (int k = 0; k < MAXV; ++k) {
+                    const int i = tid + k * TMA_THREADS;
+                    if (i < n4) {
+                        float4 v = xs4w[i];
+                        v.x = __fmul_rn(__fmul_rn(v.x, sc), gv[k].x);   // (x*s)*w, :462
+                        v.y = __fmul_rn(__fmul_rn(v.y, sc), gv[k].y);
+                        v.z = __fmul_rn(__fmul_rn(v.z, sc), gv[k].z);
+                        v.w = __fmul_rn(__fmul_rn(v.w, sc), gv[k].w);
+                        xs4w[i] = v;
+                    }
                 }
             }
         }
@@ -748,6 +866,12 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const GemvPara
             }
             if (lane == 0 && best) atomicMax(p.amax, best);
         }
+        if (EPI == EPI_XCHG) {
+            // all partial rows of this CTA are on their way: publish (system-scope release)
+            __threadfence_system();
+            __syncwarp();
+            if (lane < p.xworld && pair1 > pair0) red_release_sys_add(p.xflag_peer[lane], (unsigned int)(pair1 - pair0));
+        }
         return;
     }
 
@@ -774,7 +898,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const GemvPara
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[c_stage]);      // this warp is done with the stage
-        if (++c_stage == TMA_NSTAGE) { c_stage = 0; c_phase ^= 1; }
+        if (++c_stage == NSTAGE) { c_stage = 0; c_phase ^= 1; }
         if (st != nsteps - 1) continue;
         // ---- end of a tile: transposing butterfly, lane L (L % 4 == 0) ends with row L / 4
 #pragma unroll
@@ -929,6 +1053,7 @@ __global__ void __launch_bounds__(NT) attention_kernel(const AttnParams p) {
     float m = -INFINITY;
     for (int i = lane; i < len; i += 32) m = fmaxf(m, sc[i]);
     m = warp_max(m);
+    __syncthreads();   // every warp has read the raw scores before anyone overwrites them
     for (int i = tid; i < len; i += NT) sc[i] = expf(sc[i] - m);   // :699
     __syncthreads();
     float l = 0.0f;

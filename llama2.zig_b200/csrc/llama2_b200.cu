@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "l2b_device.cuh"
+#include "l2b_mega.cuh"
 
 using namespace l2b;
 
@@ -107,6 +108,20 @@ struct l2b_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool use_graphs = true;
     bool use_pdl = true;
+    bool use_mega = false;                   // one persistent cooperative kernel per step
+    unsigned long long *gbar = nullptr;      // its grid-barrier counter
+    int mega_nstage = 0, mega_xs_floats = 0, mega_smem = 0;
+    int last_grid = 0;                       // grid of the most recent GEMV launch
+    // fused all-reduce over peer memory (world > 1): exchange buffer [slots][world][dim] + counters
+    bool use_p2p = false;
+    float *xchg = nullptr;
+    unsigned int *xflags = nullptr;
+    float *peer_xchg[MAX_TP] = {};
+    unsigned int *peer_flags[MAX_TP] = {};
+    std::vector<void *> ipc_opened;
+    std::vector<int> xgrid;                  // producer CTAs per reduce point (same on every rank)
+    int tma_ctas_per_sm = 1;                 // CTAs of ONE TMA kernel per SM (the other half-SM is for its successor)
+    int tma_stages = 0;                      // 0 = auto (two CTAs per SM); else forced ring depth
     bool big_kernel_tma = true;              // bandwidth-bound GEMVs: TMA-ring kernel (false: register-fed 8-row kernel)
     long long gemv8_min_bytes = 8ll << 20;   // >= this many weight bytes (and n >= 1024): 8-row kernel; -1 = never
     int launches_per_step = 0;
@@ -262,6 +277,7 @@ gemv_fn gemv_pick(int tpr) {
 }
 gemv_fn gemv_pick(int epi, int tpr) {
     switch (epi) {
+    case EPI_XCHG: return gemv_pick<EPI_XCHG>(tpr);
     case EPI_STORE: return gemv_pick<EPI_STORE>(tpr);
     case EPI_ARGMAX: return gemv_pick<EPI_ARGMAX>(tpr);
     case EPI_QKV: return gemv_pick<EPI_QKV>(tpr);
@@ -295,6 +311,7 @@ int prof_mark(l2b_ctx *ctx, const char *name, int layer, uint64_t bytes, cudaStr
 
 gemv_fn gemv_tma_pick(int epi) {
     switch (epi) {
+    case EPI_XCHG: return gemv_tma_kernel<EPI_XCHG>;
     case EPI_STORE: return gemv_tma_kernel<EPI_STORE>;
     case EPI_ARGMAX: return gemv_tma_kernel<EPI_ARGMAX>;
     case EPI_QKV: return gemv_tma_kernel<EPI_QKV>;
@@ -304,6 +321,7 @@ gemv_fn gemv_tma_pick(int epi) {
 
 gemv_fn gemv8_pick(int epi) {
     switch (epi) {
+    case EPI_XCHG: return gemv8_kernel<EPI_XCHG>;
     case EPI_STORE: return gemv8_kernel<EPI_STORE>;
     case EPI_ARGMAX: return gemv8_kernel<EPI_ARGMAX>;
     case EPI_QKV: return gemv8_kernel<EPI_QKV>;
@@ -322,13 +340,21 @@ int launch_gemv(l2b_ctx *ctx, int epi, const GemvParams &p, cudaStream_t st, con
     // L2B_GEMV_BIG=ldg), latency-bound ones the fine-grained kernel
     const bool big = ctx->gemv8_min_bytes >= 0 && p.n >= 1024 &&
                      (uint64_t)p.total_rows * p.n * 4ull >= (uint64_t)ctx->gemv8_min_bytes;
-    const size_t ring = (size_t)TMA_NSTAGE * TMA_STAGE_FLOATS * 4;
-    const bool tma = big && ctx->big_kernel_tma && ring + xbytes <= (size_t)kMaxSmemOptin && p.head_size <= 256;
-    const size_t smem = tma ? ring + xbytes : xbytes;
+    // TMA-ring kernel: only x is staged in shared memory, the rest of the SM's 227 KB is the ring
+    // (measured: 5-6 stages of 32 KB on ONE CTA per SM beat 2 x 3 stages and beat leaving half
+    // the SM to the successor kernel's pre-fill; profiles/r01_tma_ring_variants.md)
+    const size_t stage_bytes = (size_t)TMA_STAGE_FLOATS * 4;
+    const size_t xonly = (size_t)p.n * 4;
+    int nstage = ctx->tma_stages > 0 ? ctx->tma_stages : (int)(((size_t)kMaxSmemOptin - xonly) / stage_bytes);
+    if (nstage > TMA_MAX_STAGES) nstage = TMA_MAX_STAGES;
+    const bool fused_ok = !(p.delta || p.gamma || p.xparts) || p.n <= 4 * TMA_THREADS * 4;   // register slices of delta/gamma
+    const bool tma = big && ctx->big_kernel_tma && nstage >= 2 && fused_ok && p.head_size <= 256 &&
+                     (size_t)nstage * stage_bytes + xonly <= (size_t)kMaxSmemOptin;
+    const size_t smem = tma ? (size_t)nstage * stage_bytes + xonly : xbytes;
     if (smem > (size_t)kMaxSmemOptin) return fail(ctx, L2B_ERR_UNSUPPORTED, "activation vector too large for shared memory");
     const int tpr = gemv_tpr(p.n);
     gemv_fn fn = tma ? gemv_tma_pick(epi) : big ? gemv8_pick(epi) : gemv_pick(epi, tpr);
-    static bool attr_done[4][8][16] = {};
+    static bool attr_done[5][8][16] = {};
     const int ti = tma ? 7 : big ? 6 : tpr == 8 ? 0 : tpr == 16 ? 1 : tpr == 32 ? 2 : tpr == 64 ? 3 : tpr == 128 ? 4 : 5;
     if (!attr_done[epi][ti][ctx->device & 15]) {
         L2B_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
@@ -338,6 +364,7 @@ int launch_gemv(l2b_ctx *ctx, int epi, const GemvParams &p, cudaStream_t st, con
     int occ = 0;
     L2B_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem));
     if (occ < 1) occ = 1;
+    if (tma && occ > ctx->tma_ctas_per_sm) occ = ctx->tma_ctas_per_sm;   // leave room for the next kernel's CTA
     int grid = ctx->num_sms * occ;
     if (big) {
         const int npairs = (p.total_rows + 1) / 2;
@@ -358,7 +385,10 @@ int launch_gemv(l2b_ctx *ctx, int epi, const GemvParams &p, cudaStream_t st, con
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at;
     lc.numAttrs = ctx->use_pdl ? 1 : 0;
-    L2B_CUDA(ctx, cudaLaunchKernelEx(&lc, fn, p));
+    GemvParams pp = p;
+    pp.nstage = nstage;
+    ctx->last_grid = grid;
+    L2B_CUDA(ctx, cudaLaunchKernelEx(&lc, fn, pp));
     ++ctx->last_launches;
     return L2B_OK;
 }
@@ -412,11 +442,27 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
         GemvParams p{};
         p.ctl = ctx->ctl;
         p.n = dim;
+        const bool p2p = ctx->world > 1 && ctx->use_p2p;
+        auto consume_slot = [&](GemvParams &g, int slot) {      // pending residual = sum of all ranks' partials
+            g.xparts = ctx->xchg + (size_t)slot * ctx->world * dim;
+            g.xflags = ctx->xflags + (size_t)slot * ctx->world;
+            g.xworld = ctx->world;
+            g.xcount_per_step = (dim + 1) / 2;     // counters count row pairs landed
+        };
+        auto produce_slot = [&](GemvParams &g, int slot) {      // my partial rows go to every rank
+            g.xworld = ctx->world;
+            for (int r = 0; r < ctx->world; ++r) {
+                g.xout_peer[r] = ctx->peer_xchg[r] + ((size_t)slot * ctx->world + ctx->rank) * dim;
+                g.xflag_peer[r] = ctx->peer_flags[r] + (size_t)slot * ctx->world + ctx->rank;
+            }
+        };
         if (l == 0) {
             p.emb = ctx->emb;                 // :295-296
+            p.bump_epoch = 1;
         } else {
             p.x_in = ctx->X[cur];
-            p.delta = ctx->delta_f;           // pending :422 of the previous layer
+            if (p2p) consume_slot(p, 2 * (l - 1) + 1);
+            else p.delta = ctx->delta_f;      // pending :422 of the previous layer
         }
         p.gamma = ctx->rms_att + (size_t)l * dim;
         p.x_out = ctx->X[cur ^ 1];
@@ -447,9 +493,11 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
         o.w0 = ctx->wo + (size_t)l * dim * ctx->q_loc;
         o.total_rows = dim; o.rows0 = dim;
         o.out0 = ctx->delta_a;
-        rc = launch_gemv(ctx, EPI_STORE, o, st, "wo", l);
+        if (p2p) produce_slot(o, 2 * l);
+        rc = launch_gemv(ctx, p2p ? EPI_XCHG : EPI_STORE, o, st, "wo", l);
         if (rc) return rc;
-        if (ctx->world > 1)
+        if (p2p) ctx->xgrid[2 * l] = ctx->last_grid;
+        else if (ctx->world > 1)
             L2B_NCCL(ctx, g_nccl.AllReduce(ctx->delta_a, ctx->delta_a, dim, ncclFloat, ncclSum, ctx->comm, st));
 
         // ---- residual + rmsnorm + w1,w3 + SiLU*mul (:395-416)
@@ -457,7 +505,8 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
         f.ctl = ctx->ctl;
         f.n = dim;
         f.x_in = ctx->X[cur];
-        f.delta = ctx->delta_a;
+        if (p2p) consume_slot(f, 2 * l);
+        else f.delta = ctx->delta_a;
         f.gamma = ctx->rms_ffn + (size_t)l * dim;
         f.x_out = ctx->X[cur ^ 1];
         cur ^= 1;
@@ -477,9 +526,11 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
         d.w0 = ctx->w2 + (size_t)l * dim * ctx->hid_loc;
         d.total_rows = dim; d.rows0 = dim;
         d.out0 = ctx->delta_f;
-        rc = launch_gemv(ctx, EPI_STORE, d, st, "w2", l);
+        if (p2p) produce_slot(d, 2 * l + 1);
+        rc = launch_gemv(ctx, p2p ? EPI_XCHG : EPI_STORE, d, st, "w2", l);
         if (rc) return rc;
-        if (ctx->world > 1)
+        if (p2p) ctx->xgrid[2 * l + 1] = ctx->last_grid;
+        else if (ctx->world > 1)
             L2B_NCCL(ctx, g_nccl.AllReduce(ctx->delta_f, ctx->delta_f, dim, ncclFloat, ncclSum, ctx->comm, st));
     }
     // ---- final residual + rmsnorm + classifier (:422-429)
@@ -487,7 +538,15 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
     k.ctl = ctx->ctl;
     k.n = dim;
     k.x_in = ctx->X[cur];
-    k.delta = ctx->delta_f;
+    if (ctx->world > 1 && ctx->use_p2p) {
+        const int slot = 2 * (c.n_layers - 1) + 1;
+        k.xparts = ctx->xchg + (size_t)slot * ctx->world * dim;
+        k.xflags = ctx->xflags + (size_t)slot * ctx->world;
+        k.xworld = ctx->world;
+        k.xcount_per_step = (dim + 1) / 2;
+    } else {
+        k.delta = ctx->delta_f;
+    }
     k.gamma = ctx->rms_final;
     k.x_out = ctx->X[cur ^ 1];
     cur ^= 1;
@@ -504,6 +563,57 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
             L2B_NCCL(ctx, g_nccl.AllReduce(ctx->amax, ctx->amax, 1, ncclUint64, ncclMax, ctx->comm, st));
         else
             L2B_NCCL(ctx, g_nccl.AllGather(ctx->logits_loc, ctx->logits, ctx->vocab_loc, ncclFloat, ctx->comm, st));
+    }
+    return L2B_OK;
+}
+
+int launch_mega(l2b_ctx *ctx, cudaStream_t st, bool want_argmax, bool do_advance) {
+    MegaParams mp{};
+    mp.emb = ctx->emb; mp.rms_att = ctx->rms_att; mp.rms_ffn = ctx->rms_ffn; mp.rms_final = ctx->rms_final;
+    mp.wq = ctx->wq; mp.wk = ctx->wk; mp.wv = ctx->wv; mp.wo = ctx->wo;
+    mp.w1 = ctx->w1; mp.w2 = ctx->w2; mp.w3 = ctx->w3; mp.wcls = ctx->wcls;
+    mp.X0 = ctx->X[0]; mp.X1 = ctx->X[1]; mp.delta_a = ctx->delta_a; mp.delta_f = ctx->delta_f;
+    mp.q = ctx->q; mp.xb = ctx->xb; mp.hb = ctx->hb;
+    mp.logits = (ctx->world > 1) ? ctx->logits_loc : ctx->logits;
+    mp.kcache = ctx->kcache; mp.vcache = ctx->vcache;
+    mp.rope_cos = ctx->rope_cos; mp.rope_sin = ctx->rope_sin;
+    mp.part_o = ctx->part_o; mp.part_ml = ctx->part_ml; mp.counters = ctx->counters;
+    mp.ctl = ctx->ctl; mp.amax = ctx->amax; mp.gbar = ctx->gbar;
+    mp.dim = ctx->dim; mp.hid_loc = ctx->hid_loc; mp.q_loc = ctx->q_loc; mp.kv_loc = ctx->kv_loc;
+    mp.heads_loc = ctx->heads_loc; mp.vocab_loc = ctx->vocab_loc; mp.n_layers = ctx->cfg.n_layers;
+    mp.seq_len = ctx->cfg.seq_len; mp.head_size = ctx->head_size; mp.kv_mul = ctx->kv_mul;
+    mp.nsplit = ctx->nsplit; mp.min_chunk = ctx->min_chunk;
+    mp.nstage = ctx->mega_nstage; mp.xs_floats = ctx->mega_xs_floats;
+    mp.want_argmax = want_argmax ? 1 : 0;
+    mp.row_base = ctx->rank * ctx->vocab_loc;
+    mp.do_advance = do_advance ? 1 : 0;
+    mp.world = ctx->world; mp.rank = ctx->rank;
+    for (int r = 0; r < ctx->world && r < MAX_TP; ++r) { mp.peer_xchg[r] = ctx->peer_xchg[r]; mp.peer_flags[r] = ctx->peer_flags[r]; }
+    mp.xchg = ctx->xchg; mp.xflags = ctx->xflags;
+    mp.forced = ctx->gen_forced; mp.out_next = ctx->gen_out; mp.n_done = ctx->gen_ndone;
+    void *args[] = {&mp};
+    L2B_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)mega_step_kernel, dim3(ctx->num_sms), dim3(MEGA_THREADS),
+                                              args, (size_t)ctx->mega_smem, st));
+    ++ctx->last_launches;
+    return L2B_OK;
+}
+
+// one decode step through the megakernel (+ the collectives a sharded context still needs)
+int enqueue_mega_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax, bool advance_after) {
+    const bool tp = ctx->world > 1;
+    int rc = launch_mega(ctx, st, want_argmax, advance_after && !tp);
+    if (rc) return rc;
+    if (tp) {
+        if (want_argmax) {
+            L2B_NCCL(ctx, g_nccl.AllReduce(ctx->amax, ctx->amax, 1, ncclUint64, ncclMax, ctx->comm, st));
+            if (advance_after) {
+                advance_kernel<<<1, 1, 0, st>>>(ctx->ctl, ctx->amax, ctx->gen_forced, ctx->gen_out, ctx->gen_ndone);
+                L2B_CUDA(ctx, cudaGetLastError());
+                ++ctx->last_launches;
+            }
+        } else {
+            L2B_NCCL(ctx, g_nccl.AllGather(ctx->logits_loc, ctx->logits, ctx->vocab_loc, ncclFloat, ctx->comm, st));
+        }
     }
     return L2B_OK;
 }
@@ -692,6 +802,38 @@ int common_create(l2b_ctx **out, const l2b_config *cfg, const Source &src, uint6
         L2B_TRY(cuda_try(cudaMemsetAsync(ctx->counters, 0, ctx->heads_loc * sizeof(unsigned int), ctx->stream), "memset"));
     }
 
+    // ---- persistent megakernel: shared-memory budget = ring + activation/attention scratch
+    {
+        L2B_TRY(dev_alloc(ctx, &ctx->gbar, (size_t)64));
+        L2B_TRY(cuda_try(cudaMemsetAsync(ctx->gbar, 0, 64 * sizeof(unsigned long long), ctx->stream), "memset"));
+        size_t xs = (size_t)ctx->dim;
+        if ((size_t)ctx->hid_loc > xs) xs = ctx->hid_loc;
+        if ((size_t)ctx->q_loc > xs) xs = ctx->q_loc;
+        const size_t attn_need = (size_t)ctx->attn_smem / sizeof(float);
+        if (attn_need > xs) xs = attn_need;
+        xs = (xs + 3) & ~(size_t)3;
+        const size_t stage_bytes = (size_t)TMA_STAGE_FLOATS * 4;
+        int ns = (int)(((size_t)kMaxSmemOptin - xs * 4) / stage_bytes);
+        if (ns > TMA_MAX_STAGES) ns = TMA_MAX_STAGES;
+        ctx->mega_nstage = ns;
+        ctx->mega_xs_floats = (int)xs;
+        ctx->mega_smem = (int)(ns * stage_bytes + xs * 4);
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        // opt-in: measured slower than the CUDA-graph + PDL chain on every workload so far
+        // (profiles/r01_megakernel.md) — the per-phase grid barrier + activation staging chain
+        // (~6 us) costs more than a PDL kernel boundary (~3.4 us)
+        const char *envm = getenv("L2B_MEGA");
+        const bool want = envm && envm[0] == '1';
+        ctx->use_mega = want && coop && ns >= 2 && hs <= 256;
+        if (ctx->use_mega) {
+            L2B_TRY(cuda_try(cudaFuncSetAttribute(mega_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin), "cudaFuncSetAttribute(mega)"));
+            int occ = 0;
+            L2B_TRY(cuda_try(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mega_step_kernel, MEGA_THREADS, ctx->mega_smem), "occupancy(mega)"));
+            if (occ < 1) ctx->use_mega = false;
+        }
+    }
+
     // ---- RoPE table (:338-342); the host's own libm values when the caller passes them
     {
         std::vector<float> hc(S * hs / 2), hsn(S * hs / 2);
@@ -732,6 +874,69 @@ int common_create(l2b_ctx **out, const l2b_config *cfg, const Source &src, uint6
         }
     }
 
+    // ---- fused all-reduce over peer memory: exchange buffers shared through CUDA IPC
+    if (world > 1) {
+        const char *mode = getenv("L2B_TP");
+        const bool want = !(mode && strcmp(mode, "nccl") == 0);
+        const size_t slots = 2 * (size_t)L;
+        ctx->xgrid.assign(slots, 0);
+        int ok = want ? 1 : 0;
+        cudaIpcMemHandle_t hx{}, hf{};
+        if (ok) {
+            L2B_TRY(dev_alloc(ctx, &ctx->xchg, slots * world * dim));
+            L2B_TRY(dev_alloc(ctx, &ctx->xflags, slots * world));
+            L2B_TRY(cuda_try(cudaMemsetAsync(ctx->xflags, 0, slots * world * sizeof(unsigned int), ctx->stream), "memset"));
+            L2B_TRY(cuda_try(cudaMemsetAsync(ctx->xchg, 0, slots * world * dim * sizeof(float), ctx->stream), "memset"));
+            if (cudaIpcGetMemHandle(&hx, ctx->xchg) != cudaSuccess || cudaIpcGetMemHandle(&hf, ctx->xflags) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+            }
+        }
+        // every rank learns every rank's handles (and whether it could make them) through NCCL
+        struct Msg { cudaIpcMemHandle_t hx, hf; int ok; int pad[3]; };
+        static_assert(sizeof(Msg) % 16 == 0, "Msg must be 16-byte sized");
+        Msg mine{hx, hf, ok, {0, 0, 0}};
+        Msg *d_all = nullptr;
+        L2B_TRY(dev_alloc(ctx, &d_all, (size_t)world));
+        L2B_TRY(cuda_try(cudaMemcpyAsync(d_all + rank, &mine, sizeof(Msg), cudaMemcpyHostToDevice, ctx->stream), "msg upload"));
+        {
+            ncclResult_t r = g_nccl.AllGather(d_all + rank, d_all, sizeof(Msg), ncclChar, ctx->comm, ctx->stream);
+            if (r != ncclSuccess) { ctx->err = "ncclAllGather(ipc handles) failed"; g_create_error = ctx->err; l2b_destroy(ctx); return L2B_ERR_COMM; }
+        }
+        std::vector<Msg> all(world);
+        L2B_TRY(cuda_try(cudaMemcpyAsync(all.data(), d_all, sizeof(Msg) * world, cudaMemcpyDeviceToHost, ctx->stream), "msg download"));
+        L2B_TRY(cuda_try(cudaStreamSynchronize(ctx->stream), "ipc exchange"));
+        for (int r = 0; r < world; ++r) ok = ok && all[r].ok;
+        if (ok) {
+            for (int r = 0; r < world && ok; ++r) {
+                if (r == rank) { ctx->peer_xchg[r] = ctx->xchg; ctx->peer_flags[r] = ctx->xflags; continue; }
+                void *px = nullptr, *pf = nullptr;
+                if (cudaIpcOpenMemHandle(&px, all[r].hx, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                    cudaIpcOpenMemHandle(&pf, all[r].hf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    ok = 0;
+                    break;
+                }
+                ctx->ipc_opened.push_back(px);
+                ctx->ipc_opened.push_back(pf);
+                ctx->peer_xchg[r] = (float *)px;
+                ctx->peer_flags[r] = (unsigned int *)pf;
+            }
+        }
+        // all ranks must take the same path: agree through a max-reduce of the failure bit
+        int *d_bad = nullptr;
+        L2B_TRY(dev_alloc(ctx, &d_bad, (size_t)1));
+        int bad = ok ? 0 : 1;
+        L2B_TRY(cuda_try(cudaMemcpyAsync(d_bad, &bad, sizeof(int), cudaMemcpyHostToDevice, ctx->stream), "flag upload"));
+        {
+            ncclResult_t r = g_nccl.AllReduce(d_bad, d_bad, 1, ncclInt, ncclMax, ctx->comm, ctx->stream);
+            if (r != ncclSuccess) { ctx->err = "ncclAllReduce(ipc agreement) failed"; g_create_error = ctx->err; l2b_destroy(ctx); return L2B_ERR_COMM; }
+        }
+        L2B_TRY(cuda_try(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "flag download"));
+        L2B_TRY(cuda_try(cudaStreamSynchronize(ctx->stream), "ipc agreement"));
+        ctx->use_p2p = (bad == 0);
+    }
+
     L2B_TRY(cuda_try(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize"));
     {
         const char *env = getenv("L2B_NO_GRAPH");
@@ -742,6 +947,10 @@ int common_create(l2b_ctx **out, const l2b_config *cfg, const Source &src, uint6
         if (env3) ctx->gemv8_min_bytes = atoll(env3);
         const char *env4 = getenv("L2B_GEMV_BIG");
         if (env4 && strcmp(env4, "ldg") == 0) ctx->big_kernel_tma = false;
+        const char *env5 = getenv("L2B_TMA_STAGES");
+        if (env5) ctx->tma_stages = atoi(env5);
+        const char *env6 = getenv("L2B_TMA_CTAS");
+        if (env6) ctx->tma_ctas_per_sm = atoi(env6) > 0 ? atoi(env6) : 1;
     }
     // one eager step of each flavour: sets function attributes outside capture and surfaces
     // launch errors before a graph hides them (it scribbles on KV row 0, rewritten by step 0)
@@ -752,6 +961,13 @@ int common_create(l2b_ctx **out, const l2b_config *cfg, const Source &src, uint6
         advance_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, ctx->amax, ctx->gen_forced, ctx->gen_out, ctx->gen_ndone);
         L2B_TRY(cuda_try(cudaStreamSynchronize(ctx->stream), "warm-up step"));
         L2B_TRY(cuda_try(cudaGetLastError(), "warm-up step"));
+        if (ctx->use_mega) {
+            set_ctl_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, 0, 0, 0, ctx->amax);
+            L2B_TRY(enqueue_mega_step(ctx, ctx->stream, false, false));
+            L2B_TRY(enqueue_mega_step(ctx, ctx->stream, true, true));
+            L2B_TRY(cuda_try(cudaStreamSynchronize(ctx->stream), "warm-up megakernel step"));
+            L2B_TRY(cuda_try(cudaGetLastError(), "warm-up megakernel step"));
+        }
     }
     if (ctx->use_graphs) L2B_TRY(build_graphs(ctx));
 #undef L2B_TRY
@@ -768,7 +984,13 @@ int run_step(l2b_ctx *ctx, int token, int pos, int which) {
         L2B_CUDA(ctx, cudaMemsetAsync(ctx->gen_forced, 0xff, sizeof(int), ctx->stream));
     set_ctl_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, token, pos, 0, ctx->amax);
     L2B_CUDA(ctx, cudaGetLastError());
-    if (ctx->use_graphs) {
+    if (ctx->use_mega) {
+        int rc = enqueue_mega_step(ctx, ctx->stream, which == 1, which == 1);
+        if (rc) return rc;
+        if (which == 0)
+            L2B_CUDA(ctx, cudaMemcpyAsync(ctx->h_logits, ctx->logits, (size_t)ctx->cfg.vocab_size * 4,
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (ctx->use_graphs) {
         L2B_CUDA(ctx, cudaGraphLaunch(which == 0 ? ctx->graph_logits : ctx->graph_argmax, ctx->stream));
         ctx->last_launches = ctx->launches_per_step + (which ? 1 : 0);
     } else {
@@ -858,6 +1080,7 @@ void l2b_destroy(l2b_ctx *ctx) {
     if (ctx->graph_argmax) cudaGraphExecDestroy(ctx->graph_argmax);
     cudaDeviceSynchronize();
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
+    for (void *p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void *p : ctx->owned) cudaFree(p);
     if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
     if (ctx->h_ints) cudaFreeHost(ctx->h_ints);
@@ -890,6 +1113,8 @@ int32_t l2b_forward(l2b_ctx *ctx, int32_t token, int32_t pos, float *host_logits
     if (!host_logits) return fail(ctx, L2B_ERR_INVALID_ARG, "host_logits is NULL");
     rc = run_step(ctx, token, pos, 0);
     if (rc) return rc;
+    // state.logits of the reference is one long-lived buffer (src/main.zig:149): copy with a
+    // streaming memcpy from the pinned landing buffer (the D2H DMA itself is part of the graph)
     memcpy(host_logits, ctx->h_logits, (size_t)ctx->cfg.vocab_size * sizeof(float));
     return L2B_OK;
 }
@@ -927,7 +1152,12 @@ int32_t l2b_generate_argmax(l2b_ctx *ctx, int32_t token, int32_t pos, int32_t n_
     for (int i = 0; i < n_steps; ++i) {
         // the whole step depends on (token,pos) only through ctl, which advance_kernel updates,
         // so the same graph is replayed back to back with no host round trip
-        if (ctx->use_graphs) {
+        if (ctx->use_mega) {
+            ctx->last_launches = 0;
+            rc = enqueue_mega_step(ctx, ctx->stream, true, true);
+            if (rc) return rc;
+            launches += ctx->last_launches;
+        } else if (ctx->use_graphs) {
             L2B_CUDA(ctx, cudaGraphLaunch(ctx->graph_argmax, ctx->stream));
             launches += ctx->launches_per_step + 1;
         } else {

@@ -203,3 +203,46 @@ def test_determinism_and_reset(l2b, stories15m):
         w, kv = t.step_bytes(0)
         assert w == 60_766_848                  # SURVEY.md 8d weight bytes per token
         assert kv == 4 * 6 * 2 * 288
+
+
+def test_megakernel_path_matches_oracle(stories15m):
+    """The opt-in persistent megakernel (L2B_MEGA=1, csrc/l2b_mega.cuh) must produce the same
+    stream and logits as the default CUDA-graph + PDL chain.  Runs in a subprocess because the
+    switch is read from the environment when a context is created."""
+    import subprocess
+    import sys
+    code = r'''
+import json, os, sys
+import numpy as np
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import llama2_zig_b200 as l2b, oracle_lib as O
+from llama2_zig_b200.checkpoint import shape_checkpoint
+gold = json.load(open("tests/golden/stories15M_t0_tokens.json"))
+ck = l2b.read_checkpoint(sys.argv[1], mmap=False)
+with l2b.Transformer(ck) as t:
+    out = t.generate_argmax(1, 0, 256, stop_on_bos=True)
+    assert out[-1] == 1 and out[:-1].tolist() == gold["tokens"], "stream differs"
+    ms, launches = t.last_timing()
+    assert launches <= 2 * len(out) + 1, launches          # one kernel per step (+ set_ctl)
+    t.reset()
+    cfg, shared, data = O.read_checkpoint(sys.argv[1])
+    om = O.OracleModel(cfg, data, shared, W=8, kind="strict")
+    tok = 1
+    for pos in range(24):
+        got, want = t.forward(tok, pos), om.forward(tok, pos)
+        assert np.max(np.abs(got - want)) / np.max(np.abs(want)) <= 1e-4
+        tok = int(np.argmax(want))
+ck2 = shape_checkpoint((768, 2048, 2, 12, 4, -512, 300)); ck2.data = l2b.synth_checkpoint_host(ck2, 9)
+om2 = O.OracleModel(O.make_config(*ck2.shape_tuple), ck2.data, ck2.shared_weights, W=8, kind="strict")
+with l2b.Transformer(ck2) as t2:
+    for pos in range(300):
+        tok = (1 + 7919 * pos) % 512
+        got = t2.forward(tok, pos); want = om2.forward(tok, pos)
+        if pos % 37 == 0 or pos > 295:
+            assert np.max(np.abs(got - want)) / np.max(np.abs(want)) <= 1e-4, pos
+print("MEGA_OK")
+'''
+    env = dict(os.environ, L2B_MEGA="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code, stories15m], capture_output=True, text=True, env=env, cwd=root, timeout=300)
+    assert r.returncode == 0 and "MEGA_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
