@@ -37,6 +37,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# rank 0 must print exactly ONE line on stdout: keep NCCL's version banner off it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 WORKLOADS = {
     #               shape key      positions  real file?
@@ -109,38 +112,51 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle's fast build (a C port of src/main.zig:285-713), one thread.
 # ----------------------------------------------------------------------------------------------
-def cpu_port_run(workload, budget_s=12.0, max_positions=None):
-    """Times the CPU port on a bounded sample of `workload`; returns the cpu_baseline dict."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as O
-    import llama2_zig_b200 as l2b
-    from llama2_zig_b200.checkpoint import shape_checkpoint
+class CpuPort:
+    """The oracle's fast build on one host core; the model is built once, samples are timed on it."""
 
-    shape_key, positions, real = WORKLOADS[workload]
-    real_path = os.path.join(ROOT, "assets", "stories15M.bin")
-    if real and os.path.exists(real_path):
-        cfg, shared, data = O.read_checkpoint(real_path, "fast")
-        forced = None
-    else:
-        ck = shape_checkpoint(shape_key)
-        cfg, shared = O.make_config(*ck.shape_tuple), ck.shared_weights
-        data = O.synth_checkpoint(cfg, shared, SYNTH_SEED[workload], "fast")
-        forced = teacher_tokens(positions, ck.vocab_size)
-    m = O.OracleModel(cfg, data, shared, W=8, kind="fast")
-    # bounded sample: as many positions as fit the budget, at most one full run
-    t0 = time.perf_counter()
-    m.forward(1, 0)
-    per_tok = time.perf_counter() - t0
-    n = positions if max_positions is None else min(positions, max_positions)
-    n = int(max(2, min(n, budget_s / max(per_tok, 1e-9))))
-    t0 = time.perf_counter()
-    calls, _, _ = m.generate(1, n, forced=None if forced is None else forced[1:n + 1], stop_on_bos=False)
-    dt = time.perf_counter() - t0
-    m.close()
-    return {"value": calls / dt, "unit": "tokens/s", "cores": 1, "kind": "port",
-            "sample": f"{calls} positions of {workload} from pos 0 (oracle -O3 -mavx2 -mfma build, W=8, 1 thread; "
-                      f"C restatement of src/main.zig:285-713, not the Zig binary)",
-            "seconds": dt}
+    def __init__(self, workload):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        from llama2_zig_b200.checkpoint import shape_checkpoint
+
+        self.workload = workload
+        shape_key, self.positions, real = WORKLOADS[workload]
+        real_path = os.path.join(ROOT, "assets", "stories15M.bin")
+        if real and os.path.exists(real_path):
+            cfg, shared, data = O.read_checkpoint(real_path, "fast")
+            self.forced = None
+        else:
+            ck = shape_checkpoint(shape_key)
+            cfg, shared = O.make_config(*ck.shape_tuple), ck.shared_weights
+            data = O.synth_checkpoint(cfg, shared, SYNTH_SEED[workload], "fast")
+            self.forced = teacher_tokens(self.positions + 1, ck.vocab_size)[1:]
+        self.m = O.OracleModel(cfg, data, shared, W=8, kind="fast")
+        t0 = time.perf_counter()
+        self.m.forward(1, 0)
+        self.per_tok = time.perf_counter() - t0
+
+    def sample(self, budget_s):
+        """Times a bounded sample (as many positions from pos 0 as fit the budget, <= one run)."""
+        n = int(max(2, min(self.positions, budget_s / max(self.per_tok, 1e-9))))
+        t0 = time.perf_counter()
+        calls, _, _ = self.m.generate(1, n, forced=None if self.forced is None else self.forced[:n],
+                                      stop_on_bos=False)
+        dt = time.perf_counter() - t0
+        return {"value": calls / dt, "unit": "tokens/s", "cores": 1, "kind": "port",
+                "sample": f"{calls} positions of {self.workload} from pos 0 (oracle -O3 -mavx2 -mfma build, W=8, "
+                          f"1 thread; C restatement of src/main.zig:285-713, not the Zig binary)",
+                "seconds": dt}
+
+    def close(self):
+        self.m.close()
+
+
+def cpu_port_run(workload, budget_s=12.0):
+    port = CpuPort(workload)
+    r = port.sample(budget_s)
+    port.close()
+    return r
 
 
 def run_reference_arm(args, rank, world):
@@ -151,13 +167,15 @@ def run_reference_arm(args, rank, world):
     positions = WORKLOADS[workload][1]
     # each step = a bounded sample of the workload, sized so the run ends within a few minutes
     budget = 8.0 if workload != "llama2-7B" else 20.0
+    port = CpuPort(workload)
     for _ in range(min(args.warmup, 1)):
-        cpu_port_run(workload, budget_s=min(2.0, budget))
-    vals, secs = [], []
+        port.sample(min(2.0, budget))
+    vals, secs, r = [], [], None
     for _ in range(max(1, min(args.steps, 3))):
-        r = cpu_port_run(workload, budget_s=budget)
+        r = port.sample(budget)
         vals.append(r["value"])
         secs.append(r["seconds"])
+    port.close()
     v = float(np.mean(vals))
     line = {"impl": "reference", "metric": "decode tokens/s", "value": v, "unit": "tokens/s",
             "n_gpus": args.gpus, "steps": len(vals), "warmup": min(args.warmup, 1),

@@ -159,6 +159,12 @@ typedef struct l2b_kernel_time {
 int32_t l2b_profile_step(l2b_ctx *ctx, int32_t token, int32_t pos, l2b_kernel_time *out,
                          int32_t cap, int32_t *n_out);
 
+/* Debug: with L2B_TRACE=1 in the environment at l2b_create time, every kernel of a step stamps
+ * %globaltimer at fixed points (entry, ring filled, dependency wait done, activations staged,
+ * first/last stage consumed, producer done, epilogue done).  Copies the last step's table
+ * [launch][512 CTAs][8 slots] (ns) to dst.                                                  */
+int32_t l2b_debug_trace(l2b_ctx *ctx, unsigned long long *dst, uint64_t cap_words, uint64_t *n_words);
+
 /* Algorithmic bytes one step at position pos must read:
  * weight bytes (this rank's shard) and KV-cache bytes.                                     */
 int32_t l2b_step_bytes(const l2b_ctx *ctx, int32_t pos, uint64_t *weight_bytes,

@@ -90,6 +90,15 @@ __device__ __forceinline__ void red_release_sys_add(unsigned int *p, unsigned in
 }
 constexpr int MAX_TP = 8;
 
+// Optional in-kernel timeline (L2B_TRACE=1): %globaltimer stamps per CTA, 8 slots per CTA.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr int TRACE_SLOTS = 8, TRACE_MAX_CTAS = 512;
+#define L2B_STAMP(tr, slot) do { if (tr) (tr)[(size_t)blockIdx.x * TRACE_SLOTS + (slot)] = global_ns(); } while (0)
+
 // ---------------------------------------------------------------------------------------
 // Block-level reductions (warp shuffles + one smem hop).  Result returned to all threads.
 // scratch: >= NWARP + 1 floats of shared memory.
@@ -203,6 +212,12 @@ struct GemvParams {
     const unsigned int *xflags;
     int xworld, xcount_per_step;
     int bump_epoch;            // set on the first kernel of a step: CTA 0 increments ctl[CTL_EPOCH]
+    // ---- L2 prefetch of the NEXT GEMV kernel's first rows (gemv_tma_kernel producer, after its own
+    // last stage is in flight): keeps HBM busy across the kernel boundary, and the successor's
+    // ring fill then hits L2.  pf_total_rows == 0 => off.
+    const float *pf_w0, *pf_w1, *pf_w2;
+    int pf_rows0, pf_rows1, pf_total_rows, pf_n, pf_epi, pf_bytes;
+    unsigned long long *trace;   // nullptr or this launch's [grid][TRACE_SLOTS] timeline
 };
 
 template <int EPI>
@@ -633,6 +648,10 @@ __global__ void __launch_bounds__(NT, 2) gemv8_kernel(const GemvParams p) {
 // BEFORE griddepcontrol.wait (weights are immutable), so the ring is already full when the
 // previous kernel finishes; 8 consumer warps read each stage with conflict-free LDS.128, share
 // one LDS.128 of x across the 8 rows, and reduce once per 8 rows (transposing butterfly).
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 constexpr int TMA_MAX_STAGES = 6;                         // ring depth is a launch parameter (GemvParams::nstage)
 constexpr int TMA_STAGE_FLOATS = GEMV8_R * NT * 4;        // 8 rows x 256 float4 = 32 KB
 constexpr int TMA_THREADS = NT + 64;                       // 8 consumer warps + producer warp + epilogue warp
@@ -669,6 +688,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
     const int total = ntiles * nsteps;
 
     if (tid == 0) {
+        L2B_STAMP(p.trace, 0);
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWARP); }
         mbar_init(&xbar, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&tile_full[s], NWARP); mbar_init(&tile_free[s], 1); }
@@ -702,6 +722,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
     if (warp == NWARP) {
         while (p_it < total && p_it < NSTAGE) produce_one();
         if (p_it >= total) pdl_launch_dependents();
+        if (lane == 0) L2B_STAMP(p.trace, 1);
     }
 
     // ---- everything below reads what earlier kernels of this step wrote
@@ -715,6 +736,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
     }
     const int pos = p.ctl[CTL_POS];
     if (p.bump_epoch && blockIdx.x == 0 && tid == 0) const_cast<int *>(p.ctl)[CTL_EPOCH] += 1;
+    if (tid == 0) L2B_STAMP(p.trace, 2);
 
     // stage the activation vector (all threads take part in the barriers of this phase).  Only x
     // goes through shared memory; the pending residual and the rmsnorm gain are read once,
@@ -766,6 +788,17 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
                 dv[k] = (i < n4) ? __ldcg(d4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
+        // the rmsnorm gain too: it is evicted from L2 by the weight stream on big models, so its
+        // DRAM round trip must overlap the x / residual fetch instead of following the reduction
+        const float4 *g4 = reinterpret_cast<const float4 *>(p.gamma);
+        float4 gv[MAXV];
+        if (p.gamma) {
+#pragma unroll
+            for (int k = 0; k < MAXV; ++k) {
+                const int i = tid + k * TMA_THREADS;
+                gv[k] = (i < n4) ? __ldg(g4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
         mbar_wait(&xbar, 0);
         if (have_delta || p.gamma || p.x_out) {
             float4 *xs4w = reinterpret_cast<float4 *>(xs);
@@ -785,13 +818,6 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
                 }
             }
             if (p.gamma) {
-                const float4 *g4 = reinterpret_cast<const float4 *>(p.gamma);
-                float4 gv[MAXV];
-#pragma unroll
-                for (int k = 0; k < MAXV; ++k) {
-                    const int i = tid + k * TMA_THREADS;
-                    gv[k] = (i < n4) ? __ldg(g4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
                 ssq = warp_sum(ssq);
                 if (lane == 0) scratch[warp] = ssq;
                 __syncthreads();
@@ -816,12 +842,34 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
         }
         __syncthreads();
     }
+    if (tid == 0) L2B_STAMP(p.trace, 3);
 
     if (warp == NWARP) {
         // ---- producer warp: keep the ring full
         while (p_it < total) {
             produce_one();
             if (p_it == total) pdl_launch_dependents();   // last stage in flight
+        }
+        if (lane == 0) L2B_STAMP(p.trace, 6);
+        // ---- then warm L2 with the first rows this CTA will stream in the NEXT GEMV kernel
+        if (p.pf_total_rows > 0 && p.pf_bytes > 0) {
+            GemvParams q;
+            q.w0 = p.pf_w0; q.w1 = p.pf_w1; q.w2 = p.pf_w2;
+            q.rows0 = p.pf_rows0; q.rows1 = p.pf_rows1; q.n = p.pf_n;
+            const int npairs_n = (p.pf_total_rows + 1) >> 1;
+            const int base_n = npairs_n / (int)gridDim.x, rem_n = npairs_n % (int)gridDim.x;
+            const int q0 = (b * base_n + min(b, rem_n)) * 2;
+            const int q1 = min((b * base_n + min(b, rem_n) + base_n + (b < rem_n ? 1 : 0)) * 2, p.pf_total_rows);
+            const int row_bytes = p.pf_n * 4;
+            int nrows = (p.pf_bytes + row_bytes - 1) / row_bytes;
+            if (nrows > q1 - q0) nrows = q1 - q0;
+            for (int r = lane; r < nrows; r += 32) {
+                const int v = q0 + r;
+                const float *rp = (p.pf_epi == EPI_QKV)    ? gemv_row_ptr<EPI_QKV>(q, v)
+                                  : (p.pf_epi == EPI_SILU) ? gemv_row_ptr<EPI_SILU>(q, v)
+                                                           : gemv_row_ptr<EPI_STORE>(q, v);
+                prefetch_l2_bulk(rp, (uint32_t)row_bytes);
+            }
         }
         return;
     }
@@ -872,6 +920,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
             __syncwarp();
             if (lane < p.xworld && pair1 > pair0) red_release_sys_add(p.xflag_peer[lane], (unsigned int)(pair1 - pair0));
         }
+        if (lane == 0) L2B_STAMP(p.trace, 7);
         return;
     }
 
@@ -889,6 +938,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
         const int v0 = r0 + t * GEMV8_R;
         const int rows = min(GEMV8_R, r1 - v0);
         mbar_wait(&full[c_stage], c_phase);
+        if (it == 0 && tid == 0) L2B_STAMP(p.trace, 4);
         if (c < n4) {
             const float4 *w4 = reinterpret_cast<const float4 *>(ring + (size_t)c_stage * TMA_STAGE_FLOATS) + tid;
             const float4 xv = xs4[c];
@@ -899,6 +949,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[c_stage]);      // this warp is done with the stage
         if (++c_stage == NSTAGE) { c_stage = 0; c_phase ^= 1; }
+        if (it == total - 1 && tid == 0) L2B_STAMP(p.trace, 5);
         if (st != nsteps - 1) continue;
         // ---- end of a tile: transposing butterfly, lane L (L % 4 == 0) ends with row L / 4
 #pragma unroll
@@ -966,6 +1017,7 @@ struct AttnParams {
     float *part_ml;        // (n_heads, nsplit, 2)
     unsigned int *counters;  // (n_heads), zero between launches
     int head_size, kv_dim, kv_mul, nsplit, min_chunk;
+    unsigned long long *trace;
 };
 
 __device__ __forceinline__ int attn_lanes_per_row(int hs4) {
@@ -1020,8 +1072,11 @@ __device__ __forceinline__ void attn_weighted_rows(float *red, const float *w, c
 __global__ void __launch_bounds__(NT) attention_kernel(const AttnParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int is_last;
+    unsigned long long *atr = p.trace ? p.trace + ((size_t)blockIdx.y * gridDim.x) * TRACE_SLOTS : nullptr;
+    if (threadIdx.x == 0) L2B_STAMP(atr, 0);
     pdl_launch_dependents();
     pdl_wait();
+    if (threadIdx.x == 0) L2B_STAMP(atr, 2);
     if (p.ctl[CTL_DONE]) return;
 
     const int h = blockIdx.x, s = blockIdx.y;
@@ -1069,6 +1124,7 @@ __global__ void __launch_bounds__(NT) attention_kernel(const AttnParams p) {
 
     if (active == 1) {
         if (tid < hs) p.xb[(size_t)h * hs + tid] = o / l;        // normalisation of :703-705
+        if (tid == 0) L2B_STAMP(atr, 7);
         return;
     }
 
@@ -1098,6 +1154,165 @@ __global__ void __launch_bounds__(NT) attention_kernel(const AttnParams p) {
         float acc = 0.0f;
         for (int j = 0; j < active; ++j) acc = fmaf(expf(ml[j * 2] - M), pb[(size_t)j * hs + tid], acc);
         p.xb[(size_t)h * hs + tid] = acc / Lsum;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// attention, flash-decoding form (default).  The three-pass kernel above has a long dependent
+// chain (scores -> barrier -> max -> barrier -> exp -> barrier -> sum -> V pass -> barrier ->
+// fold; 9.7 us per layer at pos 40 on llama2-7B, profiles/r01_trace_7b.txt).  Here every group
+// of LPR lanes owns whole timeline rows and keeps a running (max, sum, weighted V slice) in
+// registers, with the K and V loads of two rows in flight together, so the only barriers are the
+// two around the final merge of the 8 * (32/LPR) groups in shared memory.
+//   score_t = q . K_t / sqrt(hs)                                   (:367-375)
+//   online softmax: m' = max(m, s); l = l*e^(m-m') + e^(s-m'); acc = acc*e^(m-m') + e^(s-m') V_t
+//   out = sum_groups e^(m_g-M) acc_g / sum_groups e^(m_g-M) l_g    (== softmax(:687-706) . V, :657-685)
+// ---------------------------------------------------------------------------------------
+template <int NF>   // float4 per lane per row: head_size = 4 * NF * LPR
+__global__ void __launch_bounds__(NT) attention_flash_kernel(const AttnParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int is_last;
+    __shared__ float sh_L;
+    unsigned long long *atr = p.trace ? p.trace + ((size_t)blockIdx.y * gridDim.x) * TRACE_SLOTS : nullptr;
+    if (threadIdx.x == 0) L2B_STAMP(atr, 0);
+    pdl_launch_dependents();
+    pdl_wait();
+    if (threadIdx.x == 0) L2B_STAMP(atr, 2);
+    if (p.ctl[CTL_DONE]) return;
+
+    const int h = blockIdx.x, s = blockIdx.y;
+    const int hs = p.head_size, hs4 = hs >> 2;
+    const int T = p.ctl[CTL_POS] + 1;
+    int chunk = (T + p.nsplit - 1) / p.nsplit;
+    if (chunk < p.min_chunk) chunk = p.min_chunk;
+    const int active = (T + chunk - 1) / chunk;
+    if (s >= active) return;
+    const int t0 = s * chunk;
+    const int t1 = min(T, t0 + chunk);
+
+    const int LPR = hs4 / NF;                 // lanes per row (8, 4, 2 or 1)
+    const int RPW = 32 / LPR;                 // rows per warp pass
+    const int NG = NWARP * RPW;               // row groups in the CTA
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lr = lane % LPR, rw = lane / LPR;
+    const int grp = warp * RPW + rw;
+    float *accp = reinterpret_cast<float *>(smem_raw);        // [NG][hs]
+    float *mlp = accp + (size_t)NG * hs;                      // [NG][2]
+    float *wgt = mlp + 2 * NG;                                // [NG]
+
+    const size_t hoff = (size_t)(h / p.kv_mul) * hs;          // :369, :382
+    const float4 *q4 = reinterpret_cast<const float4 *>(p.q + (size_t)h * hs);
+    const float *kb = p.kcache + hoff, *vb = p.vcache + hoff;
+    const float root_hs = sqrtf((float)hs);
+
+    float4 qf[NF], acc[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        qf[f] = __ldg(q4 + lr + f * LPR);
+        acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float m = -INFINITY, l = 0.0f;
+
+    auto update = [&](const float4 (&kv)[NF], const float4 (&vv)[NF], bool valid) {
+        float sc = 0.0f;
+#pragma unroll
+        for (int f = 0; f < NF; ++f) sc = dot4(kv[f], qf[f], sc);
+        for (int o = LPR >> 1; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+        if (!valid) return;
+        sc = sc / root_hs;                                    // :372
+        const float mn = fmaxf(m, sc);
+        const float scale = expf(m - mn);                     // 0 on the first row (m = -inf)
+        const float pw = expf(sc - mn);
+        l = fmaf(l, scale, pw);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            acc[f].x = fmaf(acc[f].x, scale, pw * vv[f].x);
+            acc[f].y = fmaf(acc[f].y, scale, pw * vv[f].y);
+            acc[f].z = fmaf(acc[f].z, scale, pw * vv[f].z);
+            acc[f].w = fmaf(acc[f].w, scale, pw * vv[f].w);
+        }
+        m = mn;
+    };
+
+    // two rows per pass: 4*NF 128-bit loads in flight per lane before any arithmetic
+    // NOTE: the loop bound is warp-uniform (row groups of one warp must run the same number of
+    // passes: `update` contains full-mask shuffles); per-lane validity is handled inside.
+    for (int tbw = t0 + warp * RPW; tbw < t1; tbw += 2 * NG) {
+        const int ta = tbw + rw, tc = ta + NG;
+        const bool va = ta < t1, vc = tc < t1;
+        float4 ka[NF], vA[NF], kc[NF], vC[NF];
+        const float4 *ka4 = reinterpret_cast<const float4 *>(kb + (size_t)(va ? ta : t0) * p.kv_dim);
+        const float4 *va4 = reinterpret_cast<const float4 *>(vb + (size_t)(va ? ta : t0) * p.kv_dim);
+        const float4 *kc4 = reinterpret_cast<const float4 *>(kb + (size_t)(vc ? tc : t0) * p.kv_dim);
+        const float4 *vc4 = reinterpret_cast<const float4 *>(vb + (size_t)(vc ? tc : t0) * p.kv_dim);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            ka[f] = __ldg(ka4 + lr + f * LPR);
+            vA[f] = __ldg(va4 + lr + f * LPR);
+            kc[f] = __ldg(kc4 + lr + f * LPR);
+            vC[f] = __ldg(vc4 + lr + f * LPR);
+        }
+        update(ka, vA, va);
+        update(kc, vC, vc);
+    }
+
+    // ---- merge the NG groups (fixed order => deterministic)
+#pragma unroll
+    for (int f = 0; f < NF; ++f)
+        reinterpret_cast<float4 *>(accp + (size_t)grp * hs)[lr + f * LPR] = acc[f];
+    if (lr == 0) { mlp[2 * grp] = m; mlp[2 * grp + 1] = l; }
+    __syncthreads();
+    if (warp == 0) {
+        float M = -INFINITY;
+        for (int g = lane; g < NG; g += 32) M = fmaxf(M, mlp[2 * g]);
+        M = warp_max(M);
+        float L = 0.0f;
+        for (int g = lane; g < NG; g += 32) {
+            const float w = expf(mlp[2 * g] - M);             // empty groups: e^(-inf) = 0
+            wgt[g] = w;
+            L = fmaf(w, mlp[2 * g + 1], L);
+        }
+        L = warp_sum(L);
+        if (lane == 0) { sh_L = L; mlp[0] = M; }              // mlp[0] reused to carry M (read after the barrier)
+    }
+    __syncthreads();
+    const float L = sh_L, M = mlp[0];
+    float o = 0.0f;
+    if (tid < hs)
+        for (int g = 0; g < NG; ++g) o = fmaf(wgt[g], accp[(size_t)g * hs + tid], o);
+
+    if (active == 1) {
+        if (tid < hs) p.xb[(size_t)h * hs + tid] = o / L;
+        if (tid == 0) L2B_STAMP(atr, 7);
+        return;
+    }
+
+    // ---- several timeline splits: publish (M, L, unnormalised out), last arriver merges
+    if (tid < hs) p.part_o[((size_t)h * p.nsplit + s) * hs + tid] = o;
+    if (tid == 0) {
+        p.part_ml[((size_t)h * p.nsplit + s) * 2 + 0] = M;
+        p.part_ml[((size_t)h * p.nsplit + s) * 2 + 1] = L;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int prev = atomicAdd(&p.counters[h], 1u);
+        is_last = (prev == (unsigned int)(active - 1));
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (tid == 0) p.counters[h] = 0u;  // ready for the next launch
+    const volatile float *ml = p.part_ml + (size_t)h * p.nsplit * 2;
+    float MM = -INFINITY;
+    for (int j = 0; j < active; ++j) MM = fmaxf(MM, ml[j * 2]);
+    float Lsum = 0.0f;
+    for (int j = 0; j < active; ++j) Lsum += expf(ml[j * 2] - MM) * ml[j * 2 + 1];
+    if (tid < hs) {
+        const volatile float *pb = p.part_o + (size_t)h * p.nsplit * hs;
+        float a2 = 0.0f;
+        for (int j = 0; j < active; ++j) a2 = fmaf(expf(ml[j * 2] - MM), pb[(size_t)j * hs + tid], a2);
+        p.xb[(size_t)h * hs + tid] = a2 / Lsum;
     }
 }
 

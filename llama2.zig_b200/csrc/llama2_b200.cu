@@ -120,6 +120,10 @@ struct l2b_ctx {
     unsigned int *peer_flags[MAX_TP] = {};
     std::vector<void *> ipc_opened;
     std::vector<int> xgrid;                  // producer CTAs per reduce point (same on every rank)
+    bool attn_flash = true;                  // flash-decoding attention (false: 3-pass kernel)
+    unsigned long long *trace = nullptr;     // L2B_TRACE=1: [launch][TRACE_MAX_CTAS][TRACE_SLOTS] timeline
+    int trace_launches = 0;
+    int pf_bytes = 192 * 1024;               // per-CTA L2 prefetch of the next GEMV's first rows (0 = off)
     int tma_ctas_per_sm = 1;                 // CTAs of ONE TMA kernel per SM (the other half-SM is for its successor)
     int tma_stages = 0;                      // 0 = auto (two CTAs per SM); else forced ring depth
     bool big_kernel_tma = true;              // bandwidth-bound GEMVs: TMA-ring kernel (false: register-fed 8-row kernel)
@@ -387,10 +391,36 @@ int launch_gemv(l2b_ctx *ctx, int epi, const GemvParams &p, cudaStream_t st, con
     lc.numAttrs = ctx->use_pdl ? 1 : 0;
     GemvParams pp = p;
     pp.nstage = nstage;
+    pp.trace = (ctx->trace && !ctx->profiling) ? ctx->trace + (size_t)(ctx->last_launches % ctx->trace_launches) * TRACE_MAX_CTAS * TRACE_SLOTS : nullptr;
     ctx->last_grid = grid;
     L2B_CUDA(ctx, cudaLaunchKernelEx(&lc, fn, pp));
     ++ctx->last_launches;
     return L2B_OK;
+}
+
+// flash-decoding form when head_size/4 splits into 1..8 float4 per lane, else the 3-pass kernel
+typedef void (*attn_fn)(const AttnParams);
+attn_fn pick_attention(int head_size, bool flash, size_t *smem) {
+    const int hs4 = head_size / 4;
+    const int lpr = (hs4 % 8 == 0) ? 8 : (hs4 % 4 == 0) ? 4 : (hs4 % 2 == 0) ? 2 : 1;
+    const int nf = hs4 / lpr;
+    attn_fn f2 = nullptr;
+    if (flash) {
+        switch (nf) {
+        case 1: f2 = attention_flash_kernel<1>; break;
+        case 2: f2 = attention_flash_kernel<2>; break;
+        case 3: f2 = attention_flash_kernel<3>; break;
+        case 4: f2 = attention_flash_kernel<4>; break;
+        case 5: f2 = attention_flash_kernel<5>; break;
+        case 6: f2 = attention_flash_kernel<6>; break;
+        case 8: f2 = attention_flash_kernel<8>; break;
+        default: break;
+        }
+    }
+    if (!f2) return attention_kernel;
+    const int ng = NWARP * (32 / lpr);
+    *smem = ((size_t)ng * head_size + 3 * (size_t)ng) * sizeof(float);
+    return f2;
 }
 
 int launch_attention(l2b_ctx *ctx, int layer, cudaStream_t st) {
@@ -415,17 +445,20 @@ int launch_attention(l2b_ctx *ctx, int layer, cudaStream_t st) {
     a.kv_mul = ctx->kv_mul;
     a.nsplit = ctx->nsplit;
     a.min_chunk = ctx->min_chunk;
+    a.trace = (ctx->trace && !ctx->profiling) ? ctx->trace + (size_t)(ctx->last_launches % ctx->trace_launches) * TRACE_MAX_CTAS * TRACE_SLOTS : nullptr;
+    size_t smem = ctx->attn_smem;
+    attn_fn fn = pick_attention(ctx->head_size, ctx->attn_flash, &smem);
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(ctx->heads_loc, ctx->nsplit);
     lc.blockDim = dim3(NT);
-    lc.dynamicSmemBytes = ctx->attn_smem;
+    lc.dynamicSmemBytes = smem;
     lc.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at;
     lc.numAttrs = ctx->use_pdl ? 1 : 0;
-    L2B_CUDA(ctx, cudaLaunchKernelEx(&lc, attention_kernel, a));
+    L2B_CUDA(ctx, cudaLaunchKernelEx(&lc, fn, a));
     ++ctx->last_launches;
     return L2B_OK;
 }
@@ -437,6 +470,17 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
     const l2b_config &c = ctx->cfg;
     const int dim = ctx->dim;
     int cur = 0;
+    // weight map of the GEMV that follows a kernel, for its L2 prefetch (see GemvParams::pf_*)
+    auto set_pf = [&](GemvParams &g, int epi, const float *w0, const float *w1, const float *w2, int rows0,
+                      int rows1, int total, int n) {
+        g.pf_epi = epi; g.pf_w0 = w0; g.pf_w1 = w1; g.pf_w2 = w2;
+        g.pf_rows0 = rows0; g.pf_rows1 = rows1; g.pf_total_rows = total; g.pf_n = n;
+        g.pf_bytes = ctx->pf_bytes;
+    };
+    auto pf_qkv = [&](GemvParams &g, int l) {
+        set_pf(g, EPI_QKV, ctx->wq + (size_t)l * ctx->q_loc * dim, ctx->wk + (size_t)l * ctx->kv_loc * dim,
+               ctx->wv + (size_t)l * ctx->kv_loc * dim, ctx->q_loc, ctx->kv_loc, ctx->q_loc + 2 * ctx->kv_loc, dim);
+    };
     for (int l = 0; l < c.n_layers; ++l) {
         // ---- rmsnorm + q,k,v + RoPE + KV append (:305-358)
         GemvParams p{};
@@ -478,6 +522,7 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
         p.vcache = ctx->vcache + loff;
         p.rope_cos = ctx->rope_cos; p.rope_sin = ctx->rope_sin;
         p.head_size = ctx->head_size; p.kv_dim = ctx->kv_loc;
+        set_pf(p, EPI_STORE, ctx->wo + (size_t)l * dim * ctx->q_loc, nullptr, nullptr, dim, 0, dim, ctx->q_loc);
         int rc = launch_gemv(ctx, EPI_QKV, p, st, "qkv_rope", l);
         if (rc) return rc;
 
@@ -494,6 +539,8 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
         o.total_rows = dim; o.rows0 = dim;
         o.out0 = ctx->delta_a;
         if (p2p) produce_slot(o, 2 * l);
+        set_pf(o, EPI_SILU, ctx->w1 + (size_t)l * ctx->hid_loc * dim, ctx->w3 + (size_t)l * ctx->hid_loc * dim, nullptr,
+               ctx->hid_loc, 0, 2 * ctx->hid_loc, dim);
         rc = launch_gemv(ctx, p2p ? EPI_XCHG : EPI_STORE, o, st, "wo", l);
         if (rc) return rc;
         if (p2p) ctx->xgrid[2 * l] = ctx->last_grid;
@@ -515,6 +562,7 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
         f.rows0 = ctx->hid_loc;
         f.total_rows = 2 * ctx->hid_loc;
         f.out0 = ctx->hb;
+        set_pf(f, EPI_STORE, ctx->w2 + (size_t)l * dim * ctx->hid_loc, nullptr, nullptr, dim, 0, dim, ctx->hid_loc);
         rc = launch_gemv(ctx, EPI_SILU, f, st, "w13_silu", l);
         if (rc) return rc;
 
@@ -527,6 +575,8 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
         d.total_rows = dim; d.rows0 = dim;
         d.out0 = ctx->delta_f;
         if (p2p) produce_slot(d, 2 * l + 1);
+        if (l + 1 < c.n_layers) pf_qkv(d, l + 1);
+        else set_pf(d, EPI_STORE, ctx->wcls, nullptr, nullptr, ctx->vocab_loc, 0, ctx->vocab_loc, dim);
         rc = launch_gemv(ctx, p2p ? EPI_XCHG : EPI_STORE, d, st, "w2", l);
         if (rc) return rc;
         if (p2p) ctx->xgrid[2 * l + 1] = ctx->last_grid;
@@ -556,6 +606,7 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
     k.out0 = (ctx->world > 1) ? ctx->logits_loc : ctx->logits;
     k.amax = ctx->amax;
     k.row_base = ctx->rank * ctx->vocab_loc;
+    pf_qkv(k, 0);   // the next token starts with layer 0's q/k/v rows
     int rc = launch_gemv(ctx, want_argmax ? EPI_ARGMAX : EPI_STORE, k, st, "classifier", -1);
     if (rc) return rc;
     if (ctx->world > 1) {
@@ -949,6 +1000,16 @@ int common_create(l2b_ctx **out, const l2b_config *cfg, const Source &src, uint6
         if (env4 && strcmp(env4, "ldg") == 0) ctx->big_kernel_tma = false;
         const char *env5 = getenv("L2B_TMA_STAGES");
         if (env5) ctx->tma_stages = atoi(env5);
+        const char *enva = getenv("L2B_ATTN");
+        if (enva && strcmp(enva, "3pass") == 0) ctx->attn_flash = false;
+        const char *envt = getenv("L2B_TRACE");
+        if (envt && envt[0] == '1') {
+            ctx->trace_launches = 5 * cfg->n_layers + 2;
+            L2B_TRY(dev_alloc(ctx, &ctx->trace, (size_t)ctx->trace_launches * TRACE_MAX_CTAS * TRACE_SLOTS));
+            L2B_TRY(cuda_try(cudaMemset(ctx->trace, 0, (size_t)ctx->trace_launches * TRACE_MAX_CTAS * TRACE_SLOTS * 8), "memset"));
+        }
+        const char *env7 = getenv("L2B_PF_KB");
+        if (env7) ctx->pf_bytes = atoi(env7) * 1024;
         const char *env6 = getenv("L2B_TMA_CTAS");
         if (env6) ctx->tma_ctas_per_sm = atoi(env6) > 0 ? atoi(env6) : 1;
     }
@@ -1255,6 +1316,17 @@ int32_t l2b_profile_step(l2b_ctx *ctx, int32_t token, int32_t pos, l2b_kernel_ti
     return rc;
 }
 
+// debug: copy the in-kernel timeline of the last step (L2B_TRACE=1) to the host
+int32_t l2b_debug_trace(l2b_ctx *ctx, unsigned long long *dst, uint64_t cap_words, uint64_t *n_words) {
+    if (!ctx || !dst) return L2B_ERR_INVALID_ARG;
+    if (!ctx->trace) return fail(ctx, L2B_ERR_STATE, "tracing not enabled (L2B_TRACE=1)");
+    const uint64_t n = (uint64_t)ctx->trace_launches * TRACE_MAX_CTAS * TRACE_SLOTS;
+    if (cap_words < n) return fail(ctx, L2B_ERR_INVALID_ARG, "dst too small");
+    L2B_CUDA(ctx, cudaMemcpy(dst, ctx->trace, n * 8, cudaMemcpyDeviceToHost));
+    if (n_words) *n_words = n;
+    return L2B_OK;
+}
+
 int32_t l2b_step_bytes(const l2b_ctx *ctx, int32_t pos, uint64_t *weight_bytes, uint64_t *kv_bytes) {
     if (!ctx) return L2B_ERR_INVALID_ARG;
     const uint64_t dim = ctx->dim, L = ctx->cfg.n_layers;
@@ -1432,7 +1504,12 @@ int32_t l2b_op_attention_head(int32_t device, float *out, const float *q, const 
     const size_t smem = ((size_t)G * head_size + cap) * sizeof(float);
     if (smem > (size_t)kMaxDynSmem) { g_create_error = "n_pos too large"; return L2B_ERR_UNSUPPORTED; }
     cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-    attention_kernel<<<dim3(1, nsplit), NT, smem>>>(a);
+    {
+        const char *enva = getenv("L2B_ATTN");
+        size_t smem2 = smem;
+        attn_fn fn = pick_attention(head_size, !(enva && strcmp(enva, "3pass") == 0), &smem2);
+        fn<<<dim3(1, nsplit), NT, smem2>>>(a);
+    }
     s.down(out, dout, head_size);
     return s.rc;
 }

@@ -1,0 +1,25 @@
+#!/bin/bash
+# cautious: every stage gated on the previous one, tight timeouts
+TAG=${1:-r01l}
+OUT=gpurun_out
+mkdir -p $OUT
+timeout 90 python -m pytest tests/test_gpu_ops.py -q -m gpu -x -k "attention or matmul" > $OUT/pytest_ops_$TAG.log 2>&1 || { echo "OPS FAILED/TIMEOUT"; tail -5 $OUT/pytest_ops_$TAG.log; exit 1; }
+tail -1 $OUT/pytest_ops_$TAG.log
+timeout 300 python -m pytest tests -q -m gpu -x > $OUT/pytest_gpu_$TAG.log 2>&1 || { echo "GPU TESTS FAILED/TIMEOUT"; tail -15 $OUT/pytest_gpu_$TAG.log; exit 1; }
+tail -1 $OUT/pytest_gpu_$TAG.log
+run() { # name, workload, env...
+  name=$1; wl=$2; shift; shift
+  env "$@" timeout 150 python bench.py --workload $wl --also none --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench_${TAG}_$name.json 2> $OUT/bench_${TAG}_$name.err
+  python - <<PY
+import json
+try:
+    d=json.load(open("$OUT/bench_${TAG}_$name.json"))
+    print("$name", round(d["value"],1), "tok/s e2e", round(d["e2e"]["value"],1), "whole", round(d["whole_step"]["achieved_gbs_per_gpu"],1), "GB/s", {k: round(v["ms"]*1e3,1) for k,v in d["kernels"].items()})
+except Exception as e:
+    print("$name FAILED", e); print(open("$OUT/bench_${TAG}_$name.err").read()[-600:])
+PY
+}
+run flash7b llama2-7B L2B_X=1
+run flash15 stories15M L2B_X=1
+run flash110 stories110M L2B_X=1
+L2B_TRACE=1 timeout 120 python scripts/trace_step.py llama2-7B > $OUT/trace_7b_$TAG.txt 2>&1; tail -8 $OUT/trace_7b_$TAG.txt
