@@ -311,6 +311,11 @@ def run_workload(workload, args, rank, world, dist, sync, flush, clock_index):
     kernels = {n: {"ms": a[0] / a[2], "bytes": a[1] // a[2], "gbs": (a[1] / a[2]) / (a[0] / a[2] * 1e-3) / 1e9,
                    "launches_sampled": a[2]} for n, a in acc.items()}
     dom = max(kernels, key=lambda n: kernels[n]["bytes"] * kernels[n]["launches_sampled"])
+    traffic = None
+    try:   # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[workload][dom]["traffic"] if world == 1 else None
+    except Exception:
+        pass
     value = positions * args.steps / tot
     out = {
         "workload": workload, "positions": positions, "value": value,
@@ -320,7 +325,7 @@ def run_workload(workload, args, rank, world, dist, sync, flush, clock_index):
                 "d2h_bytes_per_step": int(d2h),
                 "path": "C++ host loop (twin of src/main.zig:995-1042) -> l2b_forward(host logits) -> host argmax"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": kernels[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": kernels[dom]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": kernels[dom]["bytes"],
                      "avg_launch_ms": kernels[dom]["ms"]},
         "whole_step": {"algorithmic_bytes_per_run_per_gpu": int(step_bytes_total),

@@ -123,7 +123,7 @@ struct l2b_ctx {
     bool attn_flash = true;                  // flash-decoding attention (false: 3-pass kernel)
     unsigned long long *trace = nullptr;     // L2B_TRACE=1: [launch][TRACE_MAX_CTAS][TRACE_SLOTS] timeline
     int trace_launches = 0;
-    int pf_bytes = 192 * 1024;               // per-CTA L2 prefetch of the next GEMV's first rows (0 = off)
+    int pf_bytes = 0;                        // per-CTA L2 prefetch of the next GEMV's first rows (L2B_PF_KB; measured: no gain)
     int tma_ctas_per_sm = 1;                 // CTAs of ONE TMA kernel per SM (the other half-SM is for its successor)
     int tma_stages = 0;                      // 0 = auto (two CTAs per SM); else forced ring depth
     bool big_kernel_tma = true;              // bandwidth-bound GEMVs: TMA-ring kernel (false: register-fed 8-row kernel)
