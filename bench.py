@@ -167,6 +167,7 @@ def run_reference_arm(args, rank, world):
     positions = WORKLOADS[workload][1]
     # each step = a bounded sample of the workload, sized so the run ends within a few minutes
     budget = 8.0 if workload != "llama2-7B" else 20.0
+    budget = float(os.environ.get("L2B_BENCH_CPU_BUDGET_S", budget))
     port = CpuPort(workload)
     for _ in range(min(args.warmup, 1)):
         port.sample(min(2.0, budget))
