@@ -1018,10 +1018,6 @@ struct AttnParams {
     unsigned int *counters;  // (n_heads), zero between launches
     int head_size, kv_dim, kv_mul, nsplit, min_chunk;
     unsigned long long *trace;
-    // experimental attention + wo fusion (attention_flash_wo_kernel)
-    const float *wo;       // this layer's (wo_rows, wo_cols) row-major matrix
-    float *wo_parts;       // (n_heads, wo_rows) partial outputs
-    int wo_rows, wo_cols;
 };
 
 __device__ __forceinline__ int attn_lanes_per_row(int hs4) {
@@ -1318,175 +1314,6 @@ __global__ void __launch_bounds__(NT) attention_flash_kernel(const AttnParams p)
         for (int j = 0; j < active; ++j) a2 = fmaf(expf(ml[j * 2] - MM), pb[(size_t)j * hs + tid], a2);
         p.xb[(size_t)h * hs + tid] = a2 / Lsum;
     }
-}
-
-// EXPERIMENTAL (L2B_FUSE_WO=1, small single-GPU models only, unmeasured at the end of round 1):
-// the attention CTA that holds head h's output multiplies it by wo's column slice of that head,
-//   part_h[r] = sum_j wo[r, h*hs + j] * out_h[j]                       (one term of :392)
-// and the NEXT kernel's prologue sums the n_heads partial vectors in head order (the same
-// consumer path the tensor-parallel exchange uses), which removes the separate wo kernel.
-__device__ __forceinline__ void attn_wo_slice(const AttnParams &p, int h, const float *out_h) {
-    const int hs4 = p.head_size >> 2;
-    const float4 *o4 = reinterpret_cast<const float4 *>(out_h);
-    for (int r = threadIdx.x; r < p.wo_rows; r += NT) {
-        const float4 *w4 = reinterpret_cast<const float4 *>(p.wo + (size_t)r * p.wo_cols + (size_t)h * p.head_size);
-        float acc = 0.0f;
-        for (int j = 0; j < hs4; ++j) acc = dot4(__ldg(w4 + j), o4[j], acc);
-        p.wo_parts[(size_t)h * p.wo_rows + r] = acc;
-    }
-}
-
-template <int NF>   // float4 per lane per row: head_size = 4 * NF * LPR
-__global__ void __launch_bounds__(NT) attention_flash_wo_kernel(const AttnParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int is_last;
-    __shared__ float sh_L;
-    unsigned long long *atr = p.trace ? p.trace + ((size_t)blockIdx.y * gridDim.x) * TRACE_SLOTS : nullptr;
-    if (threadIdx.x == 0) L2B_STAMP(atr, 0);
-    pdl_launch_dependents();
-    pdl_wait();
-    if (threadIdx.x == 0) L2B_STAMP(atr, 2);
-    if (p.ctl[CTL_DONE]) return;
-
-    const int h = blockIdx.x, s = blockIdx.y;
-    const int hs = p.head_size, hs4 = hs >> 2;
-    const int T = p.ctl[CTL_POS] + 1;
-    int chunk = (T + p.nsplit - 1) / p.nsplit;
-    if (chunk < p.min_chunk) chunk = p.min_chunk;
-    const int active = (T + chunk - 1) / chunk;
-    if (s >= active) return;
-    const int t0 = s * chunk;
-    const int t1 = min(T, t0 + chunk);
-
-    const int LPR = hs4 / NF;                 // lanes per row (8, 4, 2 or 1)
-    const int RPW = 32 / LPR;                 // rows per warp pass
-    const int NG = NWARP * RPW;               // row groups in the CTA
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int lr = lane % LPR, rw = lane / LPR;
-    const int grp = warp * RPW + rw;
-    float *accp = reinterpret_cast<float *>(smem_raw);        // [NG][hs]
-    float *mlp = accp + (size_t)NG * hs;                      // [NG][2]
-    float *wgt = mlp + 2 * NG;                                // [NG]
-
-    const size_t hoff = (size_t)(h / p.kv_mul) * hs;          // :369, :382
-    const float4 *q4 = reinterpret_cast<const float4 *>(p.q + (size_t)h * hs);
-    const float *kb = p.kcache + hoff, *vb = p.vcache + hoff;
-    const float root_hs = sqrtf((float)hs);
-
-    float4 qf[NF], acc[NF];
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-        qf[f] = __ldg(q4 + lr + f * LPR);
-        acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    float m = -INFINITY, l = 0.0f;
-
-    auto update = [&](const float4 (&kv)[NF], const float4 (&vv)[NF], bool valid) {
-        float sc = 0.0f;
-#pragma unroll
-        for (int f = 0; f < NF; ++f) sc = dot4(kv[f], qf[f], sc);
-        for (int o = LPR >> 1; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
-        if (!valid) return;
-        sc = sc / root_hs;                                    // :372
-        const float mn = fmaxf(m, sc);
-        const float scale = expf(m - mn);                     // 0 on the first row (m = -inf)
-        const float pw = expf(sc - mn);
-        l = fmaf(l, scale, pw);
-#pragma unroll
-        for (int f = 0; f < NF; ++f) {
-            acc[f].x = fmaf(acc[f].x, scale, pw * vv[f].x);
-            acc[f].y = fmaf(acc[f].y, scale, pw * vv[f].y);
-            acc[f].z = fmaf(acc[f].z, scale, pw * vv[f].z);
-            acc[f].w = fmaf(acc[f].w, scale, pw * vv[f].w);
-        }
-        m = mn;
-    };
-
-    // two rows per pass: 4*NF 128-bit loads in flight per lane before any arithmetic
-    // NOTE: the loop bound is warp-uniform (row groups of one warp must run the same number of
-    // passes: `update` contains full-mask shuffles); per-lane validity is handled inside.
-    for (int tbw = t0 + warp * RPW; tbw < t1; tbw += 2 * NG) {
-        const int ta = tbw + rw, tc = ta + NG;
-        const bool va = ta < t1, vc = tc < t1;
-        float4 ka[NF], vA[NF], kc[NF], vC[NF];
-        const float4 *ka4 = reinterpret_cast<const float4 *>(kb + (size_t)(va ? ta : t0) * p.kv_dim);
-        const float4 *va4 = reinterpret_cast<const float4 *>(vb + (size_t)(va ? ta : t0) * p.kv_dim);
-        const float4 *kc4 = reinterpret_cast<const float4 *>(kb + (size_t)(vc ? tc : t0) * p.kv_dim);
-        const float4 *vc4 = reinterpret_cast<const float4 *>(vb + (size_t)(vc ? tc : t0) * p.kv_dim);
-#pragma unroll
-        for (int f = 0; f < NF; ++f) {
-            ka[f] = __ldg(ka4 + lr + f * LPR);
-            vA[f] = __ldg(va4 + lr + f * LPR);
-            kc[f] = __ldg(kc4 + lr + f * LPR);
-            vC[f] = __ldg(vc4 + lr + f * LPR);
-        }
-        update(ka, vA, va);
-        update(kc, vC, vc);
-    }
-
-    // ---- merge the NG groups (fixed order => deterministic)
-#pragma unroll
-    for (int f = 0; f < NF; ++f)
-        reinterpret_cast<float4 *>(accp + (size_t)grp * hs)[lr + f * LPR] = acc[f];
-    if (lr == 0) { mlp[2 * grp] = m; mlp[2 * grp + 1] = l; }
-    __syncthreads();
-    if (warp == 0) {
-        float M = -INFINITY;
-        for (int g = lane; g < NG; g += 32) M = fmaxf(M, mlp[2 * g]);
-        M = warp_max(M);
-        float L = 0.0f;
-        for (int g = lane; g < NG; g += 32) {
-            const float w = expf(mlp[2 * g] - M);             // empty groups: e^(-inf) = 0
-            wgt[g] = w;
-            L = fmaf(w, mlp[2 * g + 1], L);
-        }
-        L = warp_sum(L);
-        if (lane == 0) { sh_L = L; mlp[0] = M; }              // mlp[0] reused to carry M (read after the barrier)
-    }
-    __syncthreads();
-    const float L = sh_L, M = mlp[0];
-    float o = 0.0f;
-    if (tid < hs)
-        for (int g = 0; g < NG; ++g) o = fmaf(wgt[g], accp[(size_t)g * hs + tid], o);
-
-    if (active == 1) {
-        __syncthreads();                       // everyone is done reading accp / wgt
-        if (tid < hs) accp[tid] = o / L;       // this head's attention output (the xb slice, :381-388)
-        __syncthreads();
-        attn_wo_slice(p, h, accp);
-        if (tid == 0) L2B_STAMP(atr, 7);
-        return;
-    }
-
-    // ---- several timeline splits: publish (M, L, unnormalised out), last arriver merges
-    if (tid < hs) p.part_o[((size_t)h * p.nsplit + s) * hs + tid] = o;
-    if (tid == 0) {
-        p.part_ml[((size_t)h * p.nsplit + s) * 2 + 0] = M;
-        p.part_ml[((size_t)h * p.nsplit + s) * 2 + 1] = L;
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned int prev = atomicAdd(&p.counters[h], 1u);
-        is_last = (prev == (unsigned int)(active - 1));
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    if (tid == 0) p.counters[h] = 0u;  // ready for the next launch
-    const volatile float *ml = p.part_ml + (size_t)h * p.nsplit * 2;
-    float MM = -INFINITY;
-    for (int j = 0; j < active; ++j) MM = fmaxf(MM, ml[j * 2]);
-    float Lsum = 0.0f;
-    for (int j = 0; j < active; ++j) Lsum += expf(ml[j * 2] - MM) * ml[j * 2 + 1];
-    if (tid < hs) {
-        const volatile float *pb = p.part_o + (size_t)h * p.nsplit * hs;
-        float a2 = 0.0f;
-        for (int j = 0; j < active; ++j) a2 = fmaf(expf(ml[j * 2] - MM), pb[(size_t)j * hs + tid], a2);
-        accp[tid] = a2 / Lsum;
-    }
-    __syncthreads();
-    attn_wo_slice(p, h, accp);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -120,9 +120,6 @@ struct l2b_ctx {
     unsigned int *peer_flags[MAX_TP] = {};
     std::vector<void *> ipc_opened;
     std::vector<int> xgrid;                  // producer CTAs per reduce point (same on every rank)
-    bool fuse_wo = false;                    // EXPERIMENTAL L2B_FUSE_WO=1: wo folded into the attention kernel
-    float *wo_parts = nullptr;               // (n_heads, dim) per-head partial outputs of wo
-    unsigned int *zero_flags = nullptr;      // always-satisfied counters for the consumer of wo_parts
     bool attn_flash = true;                  // flash-decoding attention (false: 3-pass kernel)
     unsigned long long *trace = nullptr;     // L2B_TRACE=1: [launch][TRACE_MAX_CTAS][TRACE_SLOTS] timeline
     int trace_launches = 0;
@@ -426,24 +423,6 @@ attn_fn pick_attention(int head_size, bool flash, size_t *smem) {
     return f2;
 }
 
-attn_fn pick_attention_wo(int head_size, size_t *smem) {
-    const int hs4 = head_size / 4;
-    const int lpr = (hs4 % 8 == 0) ? 8 : (hs4 % 4 == 0) ? 4 : (hs4 % 2 == 0) ? 2 : 1;
-    const int nf = hs4 / lpr;
-    attn_fn f2 = nullptr;
-    switch (nf) {
-    case 1: f2 = attention_flash_wo_kernel<1>; break;
-    case 2: f2 = attention_flash_wo_kernel<2>; break;
-    case 3: f2 = attention_flash_wo_kernel<3>; break;
-    case 4: f2 = attention_flash_wo_kernel<4>; break;
-    default: break;
-    }
-    if (!f2) return nullptr;
-    const int ng = NWARP * (32 / lpr);
-    *smem = ((size_t)ng * head_size + 3 * (size_t)ng) * sizeof(float);
-    return f2;
-}
-
 int launch_attention(l2b_ctx *ctx, int layer, cudaStream_t st) {
     if (ctx->profiling) {
         int hpos = 0;   // the host knows pos only through the last set_ctl; stored in n_appended-1
@@ -469,13 +448,6 @@ int launch_attention(l2b_ctx *ctx, int layer, cudaStream_t st) {
     a.trace = (ctx->trace && !ctx->profiling) ? ctx->trace + (size_t)(ctx->last_launches % ctx->trace_launches) * TRACE_MAX_CTAS * TRACE_SLOTS : nullptr;
     size_t smem = ctx->attn_smem;
     attn_fn fn = pick_attention(ctx->head_size, ctx->attn_flash, &smem);
-    if (ctx->fuse_wo) {
-        fn = pick_attention_wo(ctx->head_size, &smem);
-        a.wo = ctx->wo + (size_t)layer * ctx->dim * ctx->q_loc;
-        a.wo_parts = ctx->wo_parts;
-        a.wo_rows = ctx->dim;
-        a.wo_cols = ctx->q_loc;
-    }
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(ctx->heads_loc, ctx->nsplit);
     lc.blockDim = dim3(NT);
@@ -559,7 +531,6 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
         if (rc) return rc;
 
         // ---- wo (:392); the residual add (:395) is applied by the next kernel's prologue
-        if (!ctx->fuse_wo) {
         GemvParams o{};
         o.ctl = ctx->ctl;
         o.n = ctx->q_loc;
@@ -575,7 +546,6 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
         if (p2p) ctx->xgrid[2 * l] = ctx->last_grid;
         else if (ctx->world > 1)
             L2B_NCCL(ctx, g_nccl.AllReduce(ctx->delta_a, ctx->delta_a, dim, ncclFloat, ncclSum, ctx->comm, st));
-        }
 
         // ---- residual + rmsnorm + w1,w3 + SiLU*mul (:395-416)
         GemvParams f{};
@@ -583,13 +553,7 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
         f.n = dim;
         f.x_in = ctx->X[cur];
         if (p2p) consume_slot(f, 2 * l);
-        else if (ctx->fuse_wo) {
-            // pending residual = sum over heads of the per-head wo partials written by attention
-            f.xparts = ctx->wo_parts;
-            f.xflags = ctx->zero_flags;      // epoch * 0 == 0: satisfied at once (same GPU, kernel order)
-            f.xworld = ctx->heads_loc;
-            f.xcount_per_step = 0;
-        } else f.delta = ctx->delta_a;
+        else f.delta = ctx->delta_a;
         f.gamma = ctx->rms_ffn + (size_t)l * dim;
         f.x_out = ctx->X[cur ^ 1];
         cur ^= 1;
@@ -889,14 +853,6 @@ int common_create(l2b_ctx **out, const l2b_config *cfg, const Source &src, uint6
         L2B_TRY(dev_alloc(ctx, &ctx->part_ml, (size_t)ctx->heads_loc * ns * 2));
         L2B_TRY(dev_alloc(ctx, &ctx->counters, (size_t)ctx->heads_loc));
         L2B_TRY(cuda_try(cudaMemsetAsync(ctx->counters, 0, ctx->heads_loc * sizeof(unsigned int), ctx->stream), "memset"));
-        const char *envf = getenv("L2B_FUSE_WO");
-        size_t dummy = 0;
-        if (envf && envf[0] == '1' && world == 1 && pick_attention_wo((int)hs, &dummy)) {
-            L2B_TRY(dev_alloc(ctx, &ctx->wo_parts, (size_t)ctx->heads_loc * dim));
-            L2B_TRY(dev_alloc(ctx, &ctx->zero_flags, (size_t)ctx->heads_loc));
-            L2B_TRY(cuda_try(cudaMemsetAsync(ctx->zero_flags, 0, ctx->heads_loc * sizeof(unsigned int), ctx->stream), "memset"));
-            ctx->fuse_wo = true;
-        }
     }
 
     // ---- persistent megakernel: shared-memory budget = ring + activation/attention scratch
