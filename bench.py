@@ -6,10 +6,13 @@
          --master-port P bench.py --gpus N --steps K --warmup W
 
 Workloads (BASELINE.json `configs`):
-  stories15M   real stories15M.bin (assets/), -t 0, 256 positions    (configs[1])   default at N=1
-  stories110M  synthetic, 1024 positions, teacher-forced              (configs[2])
-  llama2-7B    synthetic fp32, 256 positions, teacher-forced          (configs[3]/[4]) default at N>1,
-               tensor-parallel over N GPUs (row/column shards + all-reduce of the hidden vector)
+  llama2-7B    synthetic fp32, 256 positions, teacher-forced          (configs[3]/[4]) THE HEADLINE AT EVERY N
+               (the metric names it and it fits one GPU, so the 1/2/4/8-GPU curve is one workload);
+               N > 1: tensor-parallel, row/column shards + all-reduce of the hidden vector fused
+               into the wo / w2 GEMV kernels over NVLink peer memory
+  stories15M   real stories15M.bin (assets/), -t 0, 256 positions    (configs[1])   under `also` at N=1
+  stories110M  synthetic, 1024 positions, teacher-forced              (configs[2])   under `also` at N=1
+`--workload X` or L2B_BENCH_WORKLOAD=X makes another workload the headline line.
 
 A "step" is ONE decode run of the workload's positions from an empty KV cache.
   value      = positions / time with everything resident in HBM: the on-device loop
@@ -49,10 +52,30 @@ WORKLOADS = {
 }
 SYNTH_SEED = {"stories15M": 15, "stories110M": 110, "llama2-7B": 7}
 L2_FLUSH_BYTES = 256 << 20   # > 126 MB L2
+SYNTH_DESC = "synthetic (counter-based N(0,s) weights, same generator on GPU and CPU; teacher-forced tokens)"
 
 
 def teacher_tokens(n, vocab):
     return np.array([(1 + 7919 * p) % vocab for p in range(n)], dtype=np.int32)
+
+
+def bench_config(workload, positions, world):
+    """The `config` object of the JSON line: identical keys and values for the GPU arm and the
+    reference arm (the driver compares them)."""
+    return {"workload": workload, "positions_per_step": positions, "temperature": 0,
+            "parallelism": "tp%d" % world if world > 1 else "single GPU",
+            "l2": "L2 flushed (256 MiB memset) before every timed step" if workload != "llama2-7B"
+                  else "inputs (26 GB of weights) exceed L2; L2 also flushed before every timed step",
+            "step": "one decode run of positions_per_step positions from an empty KV cache"}
+
+
+def pick_workload(args):
+    w = args.workload
+    if w == "auto":
+        w = os.environ.get("L2B_BENCH_WORKLOAD", "llama2-7B")
+    if w not in WORKLOADS:
+        raise SystemExit(f"unknown workload {w}")
+    return w
 
 
 def measured_peak():
@@ -160,29 +183,35 @@ def cpu_port_run(workload, budget_s=12.0):
 
 
 def run_reference_arm(args, rank, world):
-    """--impl reference: the reference's CPU implementation (the port) on the host cores."""
+    """--impl reference: the reference's CPU implementation of the path (the C port; the Zig binary
+    cannot be built here) on the host, same workload / config / metric as the GPU arm.  A step is a
+    bounded SAMPLE of the workload (the first n positions of the run) so that `--steps K --warmup W`
+    ends within a few minutes; tokens/s is per sample, ms_per_step is scaled to the full run."""
     if rank != 0:
         return
-    workload = args.workload if args.workload != "auto" else ("stories15M" if args.gpus == 1 else "llama2-7B")
+    workload = pick_workload(args)
     positions = WORKLOADS[workload][1]
-    # each step = a bounded sample of the workload, sized so the run ends within a few minutes
-    budget = 8.0 if workload != "llama2-7B" else 20.0
-    budget = float(os.environ.get("L2B_BENCH_CPU_BUDGET_S", budget))
+    total_budget = float(os.environ.get("L2B_BENCH_CPU_BUDGET_S", 150.0))
+    warmup = max(args.warmup, 0)
+    budget = total_budget / max(1, args.steps + warmup)
     port = CpuPort(workload)
-    for _ in range(min(args.warmup, 1)):
-        port.sample(min(2.0, budget))
-    vals, secs, r = [], [], None
-    for _ in range(max(1, min(args.steps, 3))):
+    for _ in range(warmup):
+        port.sample(budget)
+    vals, r = [], None
+    for _ in range(args.steps):
         r = port.sample(budget)
         vals.append(r["value"])
-        secs.append(r["seconds"])
     port.close()
     v = float(np.mean(vals))
+    sampled = int(r["sample"].split()[0])
     line = {"impl": "reference", "metric": "decode tokens/s", "value": v, "unit": "tokens/s",
-            "n_gpus": args.gpus, "steps": len(vals), "warmup": min(args.warmup, 1),
-            "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic" if workload != "stories15M" else "stories15M.bin (real)",
-            "config": {"workload": workload, "positions": positions, "temperature": 0},
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": 1e3 * positions / v, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32",
+            "data": "stories15M.bin (real checkpoint, -t 0)" if workload == "stories15M"
+                    else SYNTH_DESC,
+            "config": bench_config(workload, positions, args.gpus),
+            "sampled_positions_per_step": sampled,
             "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": 1, "kind": "port", "sample": r["sample"]},
             "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -192,6 +221,30 @@ def run_reference_arm(args, rank, world):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
+def kernel_source_sha():
+    import hashlib
+    h = hashlib.sha256()
+    for fn in ("l2b_device.cuh", "llama2_b200.cu"):
+        with open(os.path.join(ROOT, "llama2.zig_b200", "csrc", fn), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(workload, kernel):
+    """roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant
+    kernel.  It can only come from an `ncu --set full` capture (never from a run under this script), so
+    it is taken from profiles/r02_traffic.json — but ONLY if that capture was made from the kernel
+    sources this run was built from (sha recorded by scripts/summarize_ncu.py); otherwise null."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        if rec.get("kernel_source_sha16") != kernel_source_sha():
+            return None, None
+        e = rec[workload][kernel]
+        return float(e["traffic"]), e.get("source")
+    except Exception:
+        return None, None
+
+
 def load_host_twin():
     import llama2_zig_b200 as l2b
     l2b.load_library()
@@ -209,6 +262,29 @@ def load_host_twin():
     lib.l2h_generate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(GenOptions), C.POINTER(C.c_int32), C.c_int32,
                                  C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(GenResult)]
     return lib, GenOptions, GenResult
+
+
+def tp_parity(t, ck, workload, rank, device, n_pos=4):
+    """Outside the timed region: logits of the tensor-parallel context against a single-GPU context
+    of the same synthetic weights that rank 0 builds beside its shard (BASELINE.json config 5:
+    "logits vs the 1-GPU run <= 1e-4 rel").  Every rank steps the TP context (lockstep)."""
+    import llama2_zig_b200 as l2b
+    from llama2_zig_b200.checkpoint import shape_checkpoint
+    toks = teacher_tokens(n_pos, ck.vocab_size)
+    t.reset()
+    tp_logits = [t.forward(int(tok), pos) for pos, tok in enumerate(toks)]
+    tp_next = [t.forward_argmax(int(tok), pos) for pos, tok in enumerate(toks)]
+    if rank != 0:
+        return None
+    worst, argmax_equal = 0.0, True
+    with l2b.Transformer(shape_checkpoint(WORKLOADS[workload][0]), synthetic_seed=SYNTH_SEED[workload], device=device) as one:
+        for pos, tok in enumerate(toks):
+            ref = one.forward(int(tok), pos)
+            worst = max(worst, float(np.max(np.abs(tp_logits[pos] - ref)) / np.max(np.abs(ref))))
+            argmax_equal = argmax_equal and int(np.argmax(ref)) == int(np.argmax(tp_logits[pos])) == int(tp_next[pos])
+    return {"vs": "single-GPU context of the same weights on rank 0's GPU", "positions": n_pos,
+            "max_rel_logit_err": worst, "tolerance": 1e-4, "argmax_equal": bool(argmax_equal),
+            "ok": bool(worst <= 1e-4 and argmax_equal)}
 
 
 def run_workload(workload, args, rank, world, dist, sync, flush, clock_index):
@@ -237,7 +313,7 @@ def run_workload(workload, args, rank, world, dist, sync, flush, clock_index):
         ck = shape_checkpoint(shape_key)
         t = l2b.Transformer(ck, synthetic_seed=SYNTH_SEED[workload], rank=rank, world_size=world,
                             device=device, comm_id=comm_id)
-        data_desc = "synthetic (counter-based N(0,s) weights generated in HBM; teacher-forced tokens)"
+        data_desc = SYNTH_DESC
         forced = teacher_tokens(positions + 1, ck.vocab_size)[1:]
 
     def device_run():
@@ -312,11 +388,7 @@ def run_workload(workload, args, rank, world, dist, sync, flush, clock_index):
     kernels = {n: {"ms": a[0] / a[2], "bytes": a[1] // a[2], "gbs": (a[1] / a[2]) / (a[0] / a[2] * 1e-3) / 1e9,
                    "launches_sampled": a[2]} for n, a in acc.items()}
     dom = max(kernels, key=lambda n: kernels[n]["bytes"] * kernels[n]["launches_sampled"])
-    traffic = None
-    try:   # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[workload][dom]["traffic"] if world == 1 else None
-    except Exception:
-        pass
+    traffic, traffic_src = ncu_traffic(workload, dom) if world == 1 else (None, None)
     value = positions * args.steps / tot
     out = {
         "workload": workload, "positions": positions, "value": value,
@@ -326,17 +398,21 @@ def run_workload(workload, args, rank, world, dist, sync, flush, clock_index):
                 "d2h_bytes_per_step": int(d2h),
                 "path": "C++ host loop (twin of src/main.zig:995-1042) -> l2b_forward(host logits) -> host argmax"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": kernels[dom]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": kernels[dom]["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "frac_of_8TBps_nominal": kernels[dom]["gbs"] / 8000.0, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": kernels[dom]["bytes"],
                      "avg_launch_ms": kernels[dom]["ms"]},
         "whole_step": {"algorithmic_bytes_per_run_per_gpu": int(step_bytes_total),
                        "achieved_gbs_per_gpu": step_bytes_total * args.steps / (dev_tot * 1e-3) / 1e9,
                        "frac_of_peak": step_bytes_total * args.steps / (dev_tot * 1e-3) / 1e9 / peak,
+                       "frac_of_8TBps_nominal": step_bytes_total * args.steps / (dev_tot * 1e-3) / 1e9 / 8000.0,
                        "note": "stories15M's 61 MB of weights stay in the 126 MB L2 after the first token"
                                if workload == "stories15M" else "weights exceed L2: HBM-served"},
         "kernels": kernels, "clocks": clocks.summary(), "data": data_desc,
         "weights_bytes_per_token_per_gpu": int(wbytes),
     }
+    if world > 1 and forced is not None:
+        out["parity"] = tp_parity(t, ck, workload, rank, device)
     t.close()
     return out
 
@@ -378,17 +454,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    workload = args.workload if args.workload != "auto" else ("stories15M" if world == 1 else "llama2-7B")
+    workload = pick_workload(args)
     clock_index = int(os.environ.get("LOCAL_RANK", 0))
     main_res = run_workload(workload, args, rank, world, dist, sync, flush, clock_index)
     also = {}
     if world == 1 and args.also != "none":
-        extra = ["stories110M", "llama2-7B"] if args.also == "auto" else [w for w in args.also.split(",") if w]
+        extra = ["stories15M", "stories110M"] if args.also == "auto" else [w for w in args.also.split(",") if w]
         for w in extra:
             if w != workload:
                 r = run_workload(w, args, rank, world, dist, sync, flush, clock_index)
                 also[w] = {k: r[k] for k in ("value", "ms_per_step", "device_ms_per_step", "e2e", "roofline",
-                                             "whole_step", "kernels", "positions")}
+                                             "whole_step", "kernels", "positions", "data")}
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -404,17 +480,15 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": main_res["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": main_res["data"],
-            "config": {"workload": workload, "positions_per_step": main_res["positions"], "temperature": 0,
-                       "parallelism": "tp%d" % world if world > 1 else "single GPU",
-                       "l2": "L2 flushed (256 MiB memset) before every timed step" if workload != "llama2-7B"
-                             else "inputs (26 GB of weights) exceed L2; L2 also flushed before every timed step",
-                       "step": "one decode run of positions_per_step positions from an empty KV cache"},
+            "config": bench_config(workload, main_res["positions"], world),
             "device_ms_per_step": main_res["device_ms_per_step"],
             "e2e": main_res["e2e"], "gpu_launches": main_res["launches"],
             "roofline": main_res["roofline"], "whole_step": main_res["whole_step"],
             "kernels": main_res["kernels"], "clocks": main_res["clocks"],
             "cpu_baseline": cpu, "also": also,
         }
+        if main_res.get("parity") is not None:
+            line["parity"] = main_res["parity"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -13,7 +13,8 @@
  *     aborts or throws across the boundary (the reference's `assert`s, e.g. :433-434,
  *     :534-540, become argument checks);
  *   - host pointers are borrowed for the duration of the call only;
- *   - one context = one GPU; not thread-safe (the reference is single-threaded);
+ *   - one context = one decode stream on 1, 2, 4 or 8 GPUs; not thread-safe (the reference is
+ *     single-threaded);
  *   - there is NO CPU fallback: if no sm_100 device is usable the call fails with
  *     L2B_ERR_CUDA / L2B_ERR_NO_DEVICE.
  */
@@ -26,7 +27,7 @@
 extern "C" {
 #endif
 
-#define L2B_ABI_VERSION 1
+#define L2B_ABI_VERSION 2
 
 typedef enum l2b_status {
     L2B_OK = 0,
@@ -35,7 +36,7 @@ typedef enum l2b_status {
     L2B_ERR_CUDA = -3,          /* a CUDA runtime call failed; see l2b_last_error()         */
     L2B_ERR_NO_DEVICE = -4,     /* no CUDA device / not compute capability 10.x             */
     L2B_ERR_OOM = -5,           /* device or pinned-host allocation failed                  */
-    L2B_ERR_COMM = -6,          /* NCCL / peer-memory setup or collective failed            */
+    L2B_ERR_COMM = -6,          /* peer-memory setup failed, or a tensor-parallel peer timed out */
     L2B_ERR_STATE = -7          /* call order violated (e.g. pos beyond what was appended)  */
 } l2b_status;
 
@@ -55,9 +56,15 @@ typedef struct l2b_config {
 /* Tensor-parallel placement of one context (BASELINE.json config 5).
  * world_size == 1 means the whole model on `device`.  For world_size in {2,4,8}
  * wq/wk/wv/w1/w3/wcls are split by output rows, wo/w2 by input columns, and the hidden
- * vector is all-reduced after wo and after w2.  One process per rank: the caller moves
- * `comm_id` (from l2b_comm_unique_id on rank 0) to every rank by its own means
- * (bench.py uses torch.distributed).                                                      */
+ * vector is all-reduced after wo and after w2 (inside the GEMV kernels, over NVLink peer
+ * memory).  Two ways to get there:
+ *   - ONE process, l2b_create(..., n_gpus): what the Zig CLI uses (`--gpus N`); nothing else
+ *     changes for the caller, every l2b_* call drives all GPUs;
+ *   - one process PER GPU, l2b_create_sharded with this struct: the caller moves `comm_id` (from
+ *     l2b_comm_unique_id on rank 0) to every rank by its own means (bench.py uses
+ *     torch.distributed) and every rank makes the same calls in the same order (lockstep: each
+ *     decode step exchanges data with every other rank; a rank that stops stepping makes the
+ *     others return L2B_ERR_COMM after a bounded wait, L2B_SPIN_TIMEOUT_MS, default 20 s).      */
 typedef struct l2b_shard {
     int32_t rank;
     int32_t world_size;
@@ -76,9 +83,13 @@ typedef struct l2b_ctx l2b_ctx;
  *   rope_cos/sin : optional (seq_len, head_size/2) tables the host computed with the
  *                  expressions of :338-342 (so RoPE is bit-identical to the host's libm);
  *                  NULL => the library computes them with the same expressions.
- *   n_gpus       : must be 1 here; multi-GPU contexts are made with l2b_create_sharded.
- * Supported shapes: dim % 4 == 0, hidden_dim % 4 == 0, head_size = dim/n_heads even and
- * a multiple of 4, n_heads % n_kv_heads == 0.  Anything else => L2B_ERR_UNSUPPORTED.       */
+ *   n_gpus       : 1, 2, 4 or 8 GPUs (devices 0..n_gpus-1) driven by this one process; for
+ *                  n_gpus > 1 the model is sharded as described at l2b_shard and the GPUs must
+ *                  be NVLink peers.  The upload streams through pinned double buffers
+ *                  (see l2b_load_stats).
+ * Supported shapes: dim % 4 == 0, hidden_dim % 4 == 0, head_size = dim/n_heads a multiple of
+ * 4 and <= 256, n_heads % n_kv_heads == 0; for n_gpus > 1 also n_kv_heads, hidden_dim/4 and
+ * vocab_size/2 divisible by n_gpus.  Anything else => L2B_ERR_UNSUPPORTED.                  */
 int32_t l2b_create(l2b_ctx **out, const l2b_config *cfg, const float *host_weights,
                    uint64_t n_floats, const float *rope_cos, const float *rope_sin,
                    int32_t n_gpus);
@@ -96,6 +107,9 @@ int32_t l2b_create_sharded(l2b_ctx **out, const l2b_config *cfg, const float *ho
  * shard may be NULL (single GPU, device 0).                                                */
 int32_t l2b_create_synthetic(l2b_ctx **out, const l2b_config *cfg, uint64_t seed,
                              const l2b_shard *shard);
+/* Same weights, one process driving n_gpus GPUs (the synthetic twin of l2b_create(.., n_gpus)). */
+int32_t l2b_create_synthetic_group(l2b_ctx **out, const l2b_config *cfg, uint64_t seed,
+                                   int32_t n_gpus);
 
 void l2b_destroy(l2b_ctx *ctx);
 
@@ -116,9 +130,29 @@ int32_t l2b_forward(l2b_ctx *ctx, int32_t token, int32_t pos, float *host_logits
 int32_t l2b_forward_argmax(l2b_ctx *ctx, int32_t token, int32_t pos, int32_t *next);
 
 /* Zero-copy variant: runs the step and returns a pointer to the library's pinned host
- * buffer of vocab_size logits (valid until the next call on this context).  A Zig host can
- * point state.logits at it once and drop the copy.                                         */
+ * buffer of vocab_size logits (valid until the next call on this context).                 */
 int32_t l2b_forward_pinned(l2b_ctx *ctx, int32_t token, int32_t pos, const float **logits);
+
+/* The library's pinned logits buffer (vocab_size floats, lives as long as the context).  A host
+ * that uses it AS state.logits (src/main.zig:149: `state.logits = l2b_logits_buffer(ctx)[0..V]`)
+ * and passes it to l2b_forward gets the logits with no second host copy: the D2H DMA of the step
+ * lands directly in it.                                                                    */
+float *l2b_logits_buffer(l2b_ctx *ctx);
+
+/* transformer() + the vocab-wide part of temperature sampling (src/main.zig:1005-1012) on the
+ * device: logits /= temperature (:1006), softmax (:1008), and for 0 < top_p < 1 the candidate
+ * prefilter of sample_top_p (:761-768: prob >= (1-top_p)/(n-1), in index order).  The random
+ * draw, the sort of the few candidates and the CDF walk stay on the host (they use the host's
+ * PRNG, :730, :788).
+ *   host_probs : vocab_size probabilities (what :1008 leaves in state.logits); may be NULL when
+ *                only the candidates are wanted, or l2b_logits_buffer(ctx) for zero copy.
+ *   cand/n_cand: for 0 < top_p < 1: *n_cand candidates (prob, index); if more than cand_cap (or
+ *                8192) passed the filter, *n_cand = -(their number) and the host filters
+ *                host_probs itself.  Ignored (may be NULL) for top_p == 0 or 1 (:1009).         */
+typedef struct l2b_prob_index { float prob; int32_t index; } l2b_prob_index;
+int32_t l2b_forward_sample(l2b_ctx *ctx, int32_t token, int32_t pos, float temperature, float top_p,
+                           float *host_probs, l2b_prob_index *cand, int32_t cand_cap,
+                           int32_t *n_cand);
 
 /* Whole temperature-0 generation loop of src/main.zig:995-1042 on the device: starts from
  * `token` at position `pos`, runs up to n_steps steps, feeds forced[i] (if forced != NULL
@@ -144,6 +178,11 @@ int32_t l2b_read_state(l2b_ctx *ctx, int32_t which, float *dst, uint64_t n, uint
 /* Device time (ms, CUDA events on the context's stream) of the last forward/generate call,
  * and how many kernels of this library it launched.                                        */
 int32_t l2b_last_timing(const l2b_ctx *ctx, float *device_ms, int32_t *kernel_launches);
+
+/* Checkpoint ingest of the last l2b_create on this context: wall time of the
+ * pinned, double-buffered upload of all weight tensors and the bytes it moved (rank 0's shard
+ * for multi-GPU contexts).                                                                  */
+int32_t l2b_load_stats(const l2b_ctx *ctx, double *upload_ms, uint64_t *upload_bytes);
 
 /* Per-kernel device times of ONE step (eager launches with a CUDA event between kernels, on
  * the context's stream), for roofline accounting: `bytes` is the algorithmic traffic of that
@@ -189,6 +228,14 @@ uint64_t l2b_checkpoint_floats(const l2b_config *cfg);
 /* matmul (src/main.zig:485-498): xout(d) = W(d,n) . x(n)                                   */
 int32_t l2b_op_matmul(int32_t device, float *xout, const float *x, const float *w, int32_t d,
                       int32_t n);
+/* The fused pieces of the hot path in isolation: xout(d) = W(d,n) . rmsnorm(x, gamma) (gamma NULL
+ * => W . x) through one GEMV kernel flavour (kernel: 0 = the library's own choice, 1 = latency
+ * kernel, 2 = register-fed 8-row streaming kernel, 3 = TMA-ring streaming kernel).  With
+ * resid_inout != NULL the result is instead accumulated into it (the residual add of :395/:422
+ * in the epilogue) and xout is ignored.                                                    */
+int32_t l2b_op_fused_matmul(int32_t device, float *xout, const float *x, const float *gamma,
+                            const float *w, float *resid_inout, int32_t d, int32_t n,
+                            int32_t kernel);
 /* rmsnorm (:432-468)                                                                       */
 int32_t l2b_op_rmsnorm(int32_t device, float *o, const float *x, const float *w, int32_t n);
 /* softmax (:687-706), in place                                                             */
@@ -201,6 +248,11 @@ int32_t l2b_op_weighted_sum_rows(int32_t device, float *xout, int32_t out_len, c
 int32_t l2b_op_attention_head(int32_t device, float *out, const float *q, const float *keys,
                               const float *values, int32_t head_size, int32_t kv_stride,
                               int32_t n_pos);
+
+/* Sampler preparation alone (:1005-1008, :761-768) on n host logits, in place (see
+ * l2b_forward_sample); *n_cand = number that passed the filter (-1 when top_p is 0 or 1).   */
+int32_t l2b_op_sample_prep(int32_t device, float *logits_inout, int32_t n, float temperature,
+                           float top_p, l2b_prob_index *cand, int32_t cand_cap, int32_t *n_cand);
 
 #ifdef __cplusplus
 }

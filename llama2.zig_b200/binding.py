@@ -31,6 +31,10 @@ class L2BKernelTime(C.Structure):
     _fields_ = [("name", C.c_char * 24), ("layer", C.c_int32), ("ms", C.c_float), ("bytes", C.c_uint64)]
 
 
+class L2BProbIndex(C.Structure):
+    _fields_ = [("prob", C.c_float), ("index", C.c_int32)]
+
+
 class L2BShard(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world_size", C.c_int32), ("device", C.c_int32),
                 ("reserved", C.c_int32), ("comm_id", C.c_uint8 * 128)]
@@ -75,6 +79,7 @@ def load_library():
                                        C.POINTER(L2BShard)]
     lib.l2b_create_synthetic.argtypes = [C.POINTER(vp), C.POINTER(L2BConfig), C.c_uint64,
                                          C.POINTER(L2BShard)]
+    lib.l2b_create_synthetic_group.argtypes = [C.POINTER(vp), C.POINTER(L2BConfig), C.c_uint64, C.c_int32]
     lib.l2b_destroy.argtypes = [vp]
     lib.l2b_destroy.restype = None
     lib.l2b_reset.argtypes = [vp]
@@ -82,6 +87,14 @@ def load_library():
     lib.l2b_forward_argmax.argtypes = [vp, C.c_int32, C.c_int32, IP]
     lib.l2b_forward_pinned.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(FP)]
     lib.l2b_generate_argmax.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, IP, C.c_int32, IP, IP]
+    lib.l2b_logits_buffer.argtypes = [vp]
+    lib.l2b_logits_buffer.restype = FP
+    lib.l2b_forward_sample.argtypes = [vp, C.c_int32, C.c_int32, C.c_float, C.c_float, FP,
+                                       C.POINTER(L2BProbIndex), C.c_int32, IP]
+    lib.l2b_load_stats.argtypes = [vp, C.POINTER(C.c_double), U64P]
+    lib.l2b_op_fused_matmul.argtypes = [C.c_int32, FP, FP, FP, FP, FP, C.c_int32, C.c_int32, C.c_int32]
+    lib.l2b_op_sample_prep.argtypes = [C.c_int32, FP, C.c_int32, C.c_float, C.c_float,
+                                       C.POINTER(L2BProbIndex), C.c_int32, IP]
     lib.l2b_last_error.argtypes = [vp]
     lib.l2b_last_error.restype = C.c_char_p
     lib.l2b_status_string.argtypes = [C.c_int32]
@@ -157,17 +170,22 @@ class Transformer:
     """
 
     def __init__(self, ck, synthetic_seed=None, rank=0, world_size=1, device=0, comm_id=None,
-                 rope_cos=None, rope_sin=None):
+                 rope_cos=None, rope_sin=None, n_gpus=1):
+        """n_gpus > 1: ONE process drives n_gpus GPUs (l2b_create(.., n_gpus)); rank/world_size:
+        one process per GPU (l2b_create_sharded)."""
         self.lib = load_library()
         self.ck = ck
         self.cfg = make_config(ck)
         self.h = C.c_void_p()
         shard = None
+        assert n_gpus == 1 or world_size == 1
         if world_size > 1 or device != 0 or rank != 0:
             shard = L2BShard(rank, world_size, device, 0)
             if comm_id is not None:
                 C.memmove(shard.comm_id, comm_id, 128)
-        if synthetic_seed is not None:
+        if synthetic_seed is not None and n_gpus > 1:
+            rc = self.lib.l2b_create_synthetic_group(C.byref(self.h), C.byref(self.cfg), synthetic_seed, n_gpus)
+        elif synthetic_seed is not None:
             rc = self.lib.l2b_create_synthetic(C.byref(self.h), C.byref(self.cfg), synthetic_seed,
                                                C.byref(shard) if shard else None)
         else:
@@ -183,7 +201,7 @@ class Transformer:
                 self._rc, rcos = _f32(rope_cos)
                 self._rs, rsin = _f32(rope_sin)
             if shard is None:
-                rc = self.lib.l2b_create(C.byref(self.h), C.byref(self.cfg), cp, data.size, rcos, rsin, 1)
+                rc = self.lib.l2b_create(C.byref(self.h), C.byref(self.cfg), cp, data.size, rcos, rsin, n_gpus)
             else:
                 rc = self.lib.l2b_create_sharded(C.byref(self.h), C.byref(self.cfg), cp, data.size, rcos,
                                                  rsin, C.byref(shard))
@@ -231,6 +249,30 @@ class Transformer:
         nxt = C.c_int32()
         _check(self.lib.l2b_forward_argmax(self.h, int(token), int(pos), C.byref(nxt)), self.h)
         return nxt.value
+
+    def logits_buffer(self):
+        """The library's pinned logits buffer as a numpy view (state.logits of the host, zero copy)."""
+        return np.ctypeslib.as_array(self.lib.l2b_logits_buffer(self.h), shape=(self.ck.vocab_size,))
+
+    def forward_sample(self, token, pos, temperature, top_p, cand_cap=8192):
+        """transformer() + logits/=T, softmax (:1005-1008) and the top-p prefilter (:761-768) on the
+        device.  Returns (probs, candidates or None); candidates is a structured array
+        (prob, index) in index order, or None when top_p is 0/1 or too many passed the filter."""
+        probs = np.empty(self.ck.vocab_size, dtype=np.float32)
+        cand = (L2BProbIndex * cand_cap)()
+        n = C.c_int32()
+        _check(self.lib.l2b_forward_sample(self.h, int(token), int(pos), float(temperature), float(top_p),
+                                           probs.ctypes.data_as(FP), cand, cand_cap, C.byref(n)), self.h)
+        if n.value <= 0:
+            return probs, None
+        arr = np.frombuffer(cand, dtype=[("prob", "<f4"), ("index", "<i4")], count=n.value).copy()
+        return probs, arr
+
+    def load_stats(self):
+        ms = C.c_double()
+        nb = C.c_uint64()
+        _check(self.lib.l2b_load_stats(self.h, C.byref(ms), C.byref(nb)), self.h)
+        return ms.value, nb.value
 
     def generate_argmax(self, token, pos, n_steps, forced=None, stop_on_bos=True):
         out = np.full(max(n_steps, 1), -1, dtype=np.int32)
@@ -286,6 +328,41 @@ def matmul(xout, x, w, device=0):
     assert xout.dtype == np.float32
     _check(load_library().l2b_op_matmul(device, xout.ctypes.data_as(FP), xp, wp, d, n))
     return xout
+
+
+def fused_matmul(x, gamma, w, d, resid=None, kernel=0, device=0):
+    """W(d,n) . rmsnorm(x, gamma) (gamma None => W . x) through one GEMV kernel flavour
+    (0 auto, 1 latency kernel, 2 register-fed streaming kernel, 3 TMA-ring kernel): the fused
+    prologue (src/main.zig:432-468 + :485-498) and, with `resid`, the fused residual add
+    (:395/:422: returns resid + W . xs) of the hot path in isolation."""
+    x, xp = _f32(x)
+    w, wp = _f32(w)
+    gp = None
+    if gamma is not None:
+        gamma, gp = _f32(gamma)
+    n = x.size
+    assert w.size == d * n
+    out = np.zeros(d, dtype=np.float32)
+    rp = None
+    if resid is not None:
+        r = np.ascontiguousarray(resid, dtype=np.float32).copy()
+        rp = r.ctypes.data_as(FP)
+    _check(load_library().l2b_op_fused_matmul(device, out.ctypes.data_as(FP), xp, gp, wp, rp, d, n, kernel))
+    return r if resid is not None else out
+
+
+def sample_prep(logits, temperature, top_p, cand_cap=8192, device=0):
+    """logits/=T, softmax, top-p prefilter on the device (src/main.zig:1005-1008, :761-768).
+    Returns (probs, candidates-or-None, n_passed)."""
+    probs = np.ascontiguousarray(logits, dtype=np.float32).copy()
+    cand = (L2BProbIndex * cand_cap)()
+    n = C.c_int32()
+    _check(load_library().l2b_op_sample_prep(device, probs.ctypes.data_as(FP), probs.size, float(temperature),
+                                             float(top_p), cand, cand_cap, C.byref(n)))
+    arr = None
+    if n.value > 0:
+        arr = np.frombuffer(cand, dtype=[("prob", "<f4"), ("index", "<i4")], count=min(n.value, cand_cap)).copy()
+    return probs, arr, n.value
 
 
 def rmsnorm(o, x, w, device=0):

@@ -79,16 +79,46 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// System-scope signalling for the fused tensor-parallel all-reduce over NVLink peer memory.
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// ---------------------------------------------------------------------------------------
+// Tensor-parallel exchange over NVLink peer memory: "LL" units (the low-latency protocol shape
+// NCCL uses for small messages).  A value travels as an 8-byte unit {fp32 bits, epoch flag}; two
+// units go out as one 16-byte posted store.  8-byte aligned 8-byte stores land atomically, so a
+// receiver that sees flag == epoch also sees the value: no fence, no separate signal, one NVLink
+// one-way trip.  `epoch` = number of decode steps started on the context (ctl[CTL_EPOCH], >= 1;
+// landing buffers start zeroed), identical on every rank because ranks step in lockstep.
+// ---------------------------------------------------------------------------------------
+constexpr int MAX_TP = 8;
+__device__ __forceinline__ void ll_store2(unsigned long long *dst_unit, float a, float b, unsigned int epoch) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst_unit), "r"(__float_as_uint(a)),
+                 "r"(epoch), "r"(__float_as_uint(b)), "r"(epoch)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 ll_load2(const unsigned long long *src_unit) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(src_unit)
+                 : "memory");
     return v;
 }
-__device__ __forceinline__ void red_release_sys_add(unsigned int *p, unsigned int v) {
-    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
-constexpr int MAX_TP = 8;
+__device__ __forceinline__ void fence_proxy_async_global() {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns();
+// Bounded spin: a dead or diverged peer must not hang the GPU.  Every 256 polls the waiter looks at
+// the clock and at ctl[CTL_ERR]; on timeout it raises CTL_ERR (the host turns that into
+// L2B_ERR_COMM after the step) and every later wait of the step returns at once.
+struct SpinGuard {
+    int *ctl;
+    unsigned long long t0, limit_ns;
+    unsigned int polls;
+    __device__ __forceinline__ bool expired();
+};
 
 // Optional in-kernel timeline (L2B_TRACE=1): %globaltimer stamps per CTA, 8 slots per CTA.
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -151,12 +181,36 @@ __device__ __forceinline__ unsigned long long argmax_key(float v, int idx) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Step control block (device memory, 8 ints):
+// Step control block (device memory, 16 ints):
 //   [0] token  [1] pos  [2] done flag (generation loop saw BOS)  [3] step index in generate
-//   [4] stop-on-BOS enabled  [5] epoch: number of decode steps started on this context (never reset;
-//       the tensor-parallel exchange counters are compared against epoch * CTAs-per-producer)
+//   [4] stop-on-BOS enabled  [5] sampler temperature, [6] sampler top-p (fp32 bits; top-p < 0 = no
+//   candidate filter), consumed by sample_prep_kernel
+//   [8] epoch: number of decode steps started on this context (never reset; it is the flag value of
+//       the tensor-parallel LL units and the multiplier of the slice counters)
+//   [9] error word: a tensor-parallel wait timed out (peer dead or out of lockstep)
+// The host writes words [0..7] through a pinned-memory copy at the head of a step graph; words
+// [8] and [9] are only ever written by the device.
 // ---------------------------------------------------------------------------------------
-enum { CTL_TOKEN = 0, CTL_POS = 1, CTL_DONE = 2, CTL_STEP = 3, CTL_STOP_ON_BOS = 4, CTL_EPOCH = 5, CTL_WORDS = 8 };
+enum { CTL_TOKEN = 0, CTL_POS = 1, CTL_DONE = 2, CTL_STEP = 3, CTL_STOP_ON_BOS = 4, CTL_TEMP = 5, CTL_TOPP = 6,
+       CTL_EPOCH = 8, CTL_ERR = 9, CTL_WORDS = 16, CTL_HOST_WORDS = 8 };
+
+__device__ __forceinline__ bool SpinGuard::expired() {
+    if ((++polls & 255u) != 0u) return false;
+    if (*reinterpret_cast<volatile int *>(ctl + CTL_ERR)) return true;
+    if (global_ns() - t0 > limit_ns) {
+        *reinterpret_cast<volatile int *>(ctl + CTL_ERR) = 1;
+        return true;
+    }
+    return false;
+}
+__device__ __forceinline__ SpinGuard spin_guard(const int *ctl, unsigned long long limit_ns) {
+    SpinGuard g;
+    g.ctl = const_cast<int *>(ctl);
+    g.t0 = global_ns();
+    g.limit_ns = limit_ns;
+    g.polls = *reinterpret_cast<volatile int *>(g.ctl + CTL_ERR) ? 255u : 0u;   // already failed: give up on the first poll
+    return g;
+}
 
 // ---------------------------------------------------------------------------------------
 // GEMV: out = W(rows, n) . xs(n), W row-major fp32 (src/main.zig:485-498, :530-605).
@@ -172,51 +226,48 @@ enum { CTL_TOKEN = 0, CTL_POS = 1, CTL_DONE = 2, CTL_STEP = 3, CTL_STOP_ON_BOS =
 // rmsnorm (src/main.zig:432-468) with the reference's rounding points (x*s)*w.
 // ---------------------------------------------------------------------------------------
 enum GemvEpi {
-    EPI_STORE = 0,   // out[v] = acc                                   (wo, w2, wcls; :392,:419,:429)
+    EPI_STORE = 0,   // out[v] = acc                                   (wcls; :429)
     EPI_ARGMAX = 1,  // EPI_STORE + device argmax                       (:715-726 fused, 8f.1)
     EPI_QKV = 2,     // RoPE on (even,odd) pairs + KV-cache append     (:308-358)
     EPI_SILU = 3,    // hb[i] = silu(w1.x) * (w3.x)                     (:405-416)
-    EPI_XCHG = 4     // tensor parallel: partial rows stored into every rank's exchange buffer (8e)
+    EPI_XCHG = 4,    // tensor parallel: partial rows sent as LL units to every rank's landing area (8e)
+    EPI_RESID = 5,   // x[v] += acc: the residual add of :395 / :422 fused into wo / w2
+    EPI_COUNT = 6
 };
 
 struct GemvParams {
     // ---- input vector / prologue
     const float *x_in;      // n floats; when emb != nullptr: row `token` of emb is used instead
     const float *emb;       // token embedding table (layer 0: x = emb[token], :295-296) or nullptr
-    const float *delta;     // pending residual (n floats) added to x_in before use, or nullptr
     const float *gamma;     // rmsnorm gain (n floats) => fused rmsnorm, or nullptr => plain staging
-    float *x_out;           // if non-null, CTA 0 writes the (residual-updated, un-normalised) x here
-    const int *ctl;         // control block (token, pos, done)
+    float *x_out;           // layer 0 only: CTA 0 copies the embedding row here (it becomes the residual stream)
+    const int *ctl;         // control block (token, pos, done, epoch, error)
     int n;                  // columns (multiple of 4)
     // ---- matrices (virtual row space depends on the epilogue)
     const float *w0, *w1, *w2;
     int rows0, rows1, rows2;  // EPI_QKV: q/k/v rows.  EPI_SILU: rows0 = hidden (virtual rows = 2*hidden)
     int total_rows;           // virtual rows
     // ---- outputs
-    float *out0;            // STORE: out; QKV: q; SILU: hb
+    float *out0;            // STORE: out; QKV: q; SILU: hb; RESID: the residual stream x (read-modify-write)
     float *kcache, *vcache; // QKV: this layer's (seq_len, kv_dim) caches
     const float *rope_cos, *rope_sin;  // (seq_len, head_size/2)
     int head_size, kv_dim;
     unsigned long long *amax;  // ARGMAX: packed running maximum (must be 0 before the launch)
-    int row_base;              // ARGMAX: global index of out row 0 (vocab shard offset)
+    int row_base;              // ARGMAX / XCHG: global index of out row 0 (vocab shard offset)
     int nstage;                // gemv_tma_kernel: ring depth (2..TMA_MAX_STAGES)
     // ---- tensor-parallel exchange (fused GEMV + all-reduce over peer memory); unused when xworld == 0
-    // producer side (EPI_XCHG): every rank's landing area for MY partial rows of this reduce point,
-    // and the counter there that my CTAs bump (system-scope release) when their rows have landed
-    float *xout_peer[MAX_TP];
-    unsigned int *xflag_peer[MAX_TP];
-    // consumer side: my landing areas (xworld x n floats, one per source rank) and counters of the
-    // reduce point whose sum is this kernel's pending residual; a source rank is complete when its
-    // counter reaches epoch * xcount_per_step (xcount_per_step = row pairs of the reduce point)
-    const float *xparts;
-    const unsigned int *xflags;
-    int xworld, xcount_per_step;
+    // producer side (EPI_XCHG): row v of my result goes, as an LL unit, to ll_out[d][row_base + v]
+    // for every destination d < ll_ndst (the landing area reserved for MY rank on that peer)
+    unsigned long long *ll_out[MAX_TP];
+    int ll_ndst;
+    // consumer side (fused-rmsnorm kernels): x_in is the residual stream; before staging it, the
+    // partial rows of all xworld ranks (ll_in[r * n + i]) are added into it, slice by slice, by the
+    // first ceil(n/128) CTAs; rdone counts finished slices (monotonic: epoch * slices when complete)
+    const unsigned long long *ll_in;
+    unsigned int *rdone;
+    int xworld;
     int bump_epoch;            // set on the first kernel of a step: CTA 0 increments ctl[CTL_EPOCH]
-    // ---- L2 prefetch of the NEXT GEMV kernel's first rows (gemv_tma_kernel producer, after its own
-    // last stage is in flight): keeps HBM busy across the kernel boundary, and the successor's
-    // ring fill then hits L2.  pf_total_rows == 0 => off.
-    const float *pf_w0, *pf_w1, *pf_w2;
-    int pf_rows0, pf_rows1, pf_total_rows, pf_n, pf_epi, pf_bytes;
+    unsigned long long spin_ns;  // bound on every peer wait (SpinGuard)
     unsigned long long *trace;   // nullptr or this launch's [grid][TRACE_SLOTS] timeline
 };
 
@@ -235,55 +286,75 @@ __device__ __forceinline__ const float *gemv_row_ptr(const GemvParams &p, int v)
     }
 }
 
-// ---- shared prologue: stage the activation vector (+ residual, + rmsnorm) into shared memory.
+// ---- tensor-parallel all-reduce, consumer half.  Called by every thread of a fused-rmsnorm
+// kernel after griddepcontrol.wait.  The residual stream x (p.x_in) is updated IN PLACE:
+//   x[i] += sum_r partial_r[i]   (fixed rank order: every rank forms bit-identical x)
+// Work is cut into slices of 32 float4; slice s belongs to warp 0 of CTA (s mod grid), which polls
+// the LL units of that slice (they arrive straight from the producers' epilogues over NVLink),
+// writes the new x slice and bumps `rdone`.  Every CTA then waits until all slices of this step are
+// done, so the 148 CTAs read 16 KB of finished x instead of 148 x g x 16 KB of partials.
+constexpr int TP_SLICE4 = 32;
+__device__ __forceinline__ void tp_reduce_into_x(const GemvParams &p) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n4 = p.n >> 2;
+    const int nslices = (n4 + TP_SLICE4 - 1) / TP_SLICE4;
+    const unsigned int epoch = (unsigned int)p.ctl[CTL_EPOCH];
+    if (tid < 32) {
+        SpinGuard sg = spin_guard(p.ctl, p.spin_ns);
+        float4 *x4 = reinterpret_cast<float4 *>(const_cast<float *>(p.x_in));
+        for (int s = blockIdx.x; s < nslices; s += gridDim.x) {
+            const int i = s * TP_SLICE4 + lane;
+            if (i < n4) {
+                float4 v = __ldcg(x4 + i);
+                for (int r = 0; r < p.xworld; ++r) {
+                    const unsigned long long *u = p.ll_in + (size_t)r * p.n + (size_t)i * 4;
+                    uint4 a = ll_load2(u), b = ll_load2(u + 2);
+                    while (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch) {
+                        if (sg.expired()) break;
+                        a = ll_load2(u);
+                        b = ll_load2(u + 2);
+                    }
+                    v.x += __uint_as_float(a.x); v.y += __uint_as_float(a.z);   // accum(), :708-713
+                    v.z += __uint_as_float(b.x); v.w += __uint_as_float(b.z);
+                }
+                __stcg(x4 + i, v);
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(p.rdone, 1u);
+        }
+        if (lane == 0) {
+            const unsigned int want = epoch * (unsigned int)nslices;
+            while ((int)(ld_acquire_gpu(p.rdone) - want) < 0)
+                if (sg.expired()) break;
+            fence_proxy_async_global();   // x is about to be read through the TMA (async proxy)
+        }
+    }
+    __syncthreads();
+}
+
+// ---- shared prologue: stage the activation vector (+ rmsnorm) into shared memory.
 // Must be called by all NT threads after pdl_wait(); thread 0 has already initialised `bar`.
 __device__ __forceinline__ void gemv_stage_input(const GemvParams &p, float *xs, float *aux,
                                                  uint64_t *bar, float *scratch) {
     const int tid = threadIdx.x;
     const int n4 = p.n >> 2;
+    if (p.ll_in) tp_reduce_into_x(p);
     const float *xsrc = p.emb ? p.emb + (size_t)p.ctl[CTL_TOKEN] * p.n : p.x_in;
-    float *ds = aux;
-    float *gs = p.delta ? aux + p.n : aux;
+    float *gs = aux;
     if (tid == 0) {
         const uint32_t bytes = (uint32_t)p.n * 4u;
-        mbar_expect_tx(bar, bytes * (1u + (p.delta ? 1u : 0u) + (p.gamma ? 1u : 0u)));
+        mbar_expect_tx(bar, bytes * (1u + (p.gamma ? 1u : 0u)));
         tma_load_1d(xs, xsrc, bytes, bar);
-        if (p.delta) tma_load_1d(ds, p.delta, bytes, bar);
         if (p.gamma) tma_load_1d(gs, p.gamma, bytes, bar);
     }
-    if (p.xparts) {
-        // fused all-reduce, consumer half: wait until every rank's partial rows have landed here
-        if (tid < p.xworld) {
-            const unsigned int want = (unsigned int)p.ctl[CTL_EPOCH] * (unsigned int)p.xcount_per_step;
-            while ((int)(ld_acquire_sys(p.xflags + tid) - want) < 0) { }
-        }
-    }
-    __syncthreads();  // barrier init visible to all waiters; exchange data visible to all threads
+    __syncthreads();  // barrier init visible to all waiters
     mbar_wait(bar, 0);
-    if (p.xparts) {
+    if (p.gamma || p.x_out) {
         float4 *xs4 = reinterpret_cast<float4 *>(xs);
-        const float4 *pp = reinterpret_cast<const float4 *>(p.xparts);
-        for (int i = tid; i < n4; i += NT) {
-            float4 v = xs4[i];
-            for (int r = 0; r < p.xworld; ++r) {          // fixed rank order: every rank gets the same x
-                const float4 d = __ldcg(pp + (size_t)r * n4 + i);
-                v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
-            }
-            xs4[i] = v;
-        }
-        __syncthreads();
-    }
-    if (p.delta || p.gamma || p.x_out) {
-        float4 *xs4 = reinterpret_cast<float4 *>(xs);
-        const float4 *ds4 = reinterpret_cast<const float4 *>(ds);
         float ssq = 0.0f;
         for (int i = tid; i < n4; i += NT) {
-            float4 v = xs4[i];
-            if (p.delta) {
-                const float4 d = ds4[i];
-                v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;   // accum(), :708-713
-                xs4[i] = v;
-            }
+            const float4 v = xs4[i];
             if (p.x_out && blockIdx.x == 0) reinterpret_cast<float4 *>(p.x_out)[i] = v;
             ssq = fmaf(v.x, v.x, ssq); ssq = fmaf(v.y, v.y, ssq);
             ssq = fmaf(v.z, v.z, ssq); ssq = fmaf(v.w, v.w, ssq);
@@ -308,17 +379,21 @@ __device__ __forceinline__ void gemv_stage_input(const GemvParams &p, float *xs,
     }
 }
 
-// ---- shared epilogue for one adjacent pair of virtual rows (v0 even)
+// ---- shared epilogue for one adjacent pair of virtual rows (v0 even).  `xr` is the pair of
+// residual-stream values the caller prefetched for EPI_RESID (ignored otherwise).
 template <int EPI>
 __device__ __forceinline__ void gemv_epilogue_pair(const GemvParams &p, int v0, float a0, float a1,
-                                                   int pos, unsigned long long &best) {
+                                                   int pos, unsigned long long &best, unsigned int epoch,
+                                                   float2 xr) {
     if (v0 >= p.total_rows) return;
     if (EPI == EPI_XCHG) {
-        // my partial of rows (v0, v0+1) goes to every rank (incl. me) over NVLink: posted stores
-        for (int r = 0; r < p.xworld; ++r) {
-            if (v0 + 1 < p.total_rows) *reinterpret_cast<float2 *>(p.xout_peer[r] + v0) = make_float2(a0, a1);
-            else p.xout_peer[r][v0] = a0;
-        }
+        // my partial of rows (v0, v0+1) goes to every destination over NVLink as one 16-byte posted
+        // store of two LL units (total_rows is even for every exchanged shape: dim % 4 == 0)
+        for (int d = 0; d < p.ll_ndst; ++d) ll_store2(p.ll_out[d] + p.row_base + v0, a0, a1, epoch);
+    } else if (EPI == EPI_RESID) {
+        // accum(), :708-713, applied by the producer: each row of x has exactly one owner
+        if (v0 + 1 < p.total_rows) *reinterpret_cast<float2 *>(p.out0 + v0) = make_float2(xr.x + a0, xr.y + a1);
+        else p.out0[v0] = xr.x + a0;
     } else if (EPI == EPI_STORE || EPI == EPI_ARGMAX) {
         p.out0[v0] = a0;
         if (v0 + 1 < p.total_rows) p.out0[v0 + 1] = a1;
@@ -353,6 +428,17 @@ __device__ __forceinline__ void gemv_epilogue_pair(const GemvParams &p, int v0, 
     }
 }
 
+// residual-stream values of rows (v0, v0+1) for EPI_RESID, fetched ahead of the reduction
+template <int EPI>
+__device__ __forceinline__ float2 gemv_resid_fetch(const GemvParams &p, int v0) {
+    float2 r = make_float2(0.f, 0.f);
+    if (EPI == EPI_RESID && v0 < p.total_rows) {
+        if (v0 + 1 < p.total_rows) r = __ldcg(reinterpret_cast<const float2 *>(p.out0 + v0));
+        else r.x = __ldcg(p.out0 + v0);
+    }
+    return r;
+}
+
 template <int EPI>
 __device__ __forceinline__ void gemv_finish_argmax(const GemvParams &p, unsigned long long best,
                                                    unsigned long long *blk_key) {
@@ -363,19 +449,6 @@ __device__ __forceinline__ void gemv_finish_argmax(const GemvParams &p, unsigned
     if (best) atomicMax(blk_key, best);
     __syncthreads();
     if (threadIdx.x == 0 && *blk_key) atomicMax(p.amax, *blk_key);
-}
-
-// Producer half of the fused all-reduce for the block-structured kernels: every thread that stored
-// partial rows fences at system scope, then one thread per destination rank bumps that rank's
-// counter for (reduce point, this rank).
-// The counters count ROW PAIRS landed (not CTAs), so one step always adds ceil(rows/2) per
-// (reduce point, source rank) whichever kernel flavour or grid size produced them.
-template <int EPI>
-__device__ __forceinline__ void gemv_finish_xchg(const GemvParams &p, unsigned int my_pairs) {
-    if (EPI != EPI_XCHG) return;
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < p.xworld && my_pairs) red_release_sys_add(p.xflag_peer[threadIdx.x], my_pairs);
 }
 
 // ---- v1: small / latency-bound shapes.  TPR threads per pair of rows, tiles strided over CTAs.
@@ -436,12 +509,16 @@ __global__ void __launch_bounds__(NT) gemv_kernel(const GemvParams p) {
 
     const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
     const int pos = p.ctl[CTL_POS];
+    const unsigned int epoch = (EPI == EPI_XCHG) ? (unsigned int)p.ctl[CTL_EPOCH] : 0u;
     unsigned long long best = 0ull;
+    float2 xr = make_float2(0.f, 0.f);
     float acc[GEMV_R];
 #pragma unroll
     for (int r = 0; r < GEMV_R; ++r) acc[r] = 0.0f;
 
     while (tile < ntiles) {
+        if (EPI == EPI_RESID && chunk == 0 && sub == 0)   // residual values of this tile's rows, in flight during the dot products
+            xr = gemv_resid_fetch<EPI>(p, tile * TILE_ROWS + grp * GEMV_R);
         // ---- consume the chunk in registers
 #pragma unroll
         for (int u = 0; u < GEMV_U; ++u) {
@@ -492,7 +569,7 @@ __global__ void __launch_bounds__(NT) gemv_kernel(const GemvParams p) {
                 }
             }
             if (sub == 0)
-                gemv_epilogue_pair<EPI>(p, tile * TILE_ROWS + grp * GEMV_R, acc[0], acc[1], pos, best);
+                gemv_epilogue_pair<EPI>(p, tile * TILE_ROWS + grp * GEMV_R, acc[0], acc[1], pos, best, epoch, xr);
 #pragma unroll
             for (int r = 0; r < GEMV_R; ++r) acc[r] = 0.0f;
         }
@@ -501,13 +578,6 @@ __global__ void __launch_bounds__(NT) gemv_kernel(const GemvParams p) {
     }
     if (!triggered) pdl_launch_dependents();
     gemv_finish_argmax<EPI>(p, best, &blk_key);
-    if (EPI == EPI_XCHG) {
-        const int npairs_all = (p.total_rows + 1) >> 1;
-        unsigned int mine = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
-            mine += (unsigned int)max(0, min(GROUPS, npairs_all - t * GROUPS));
-        gemv_finish_xchg<EPI>(p, mine);
-    }
 }
 
 // ---- v2: bandwidth-bound shapes (n >= 1024, many MB).  The whole CTA (256 threads) walks the
@@ -570,7 +640,9 @@ __global__ void __launch_bounds__(NT, 2) gemv8_kernel(const GemvParams p) {
 
     const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
     const int pos = p.ctl[CTL_POS];
+    const unsigned int epoch = (EPI == EPI_XCHG) ? (unsigned int)p.ctl[CTL_EPOCH] : 0u;
     unsigned long long best = 0ull;
+    float2 xr = make_float2(0.f, 0.f);
     float acc[GEMV8_R];
 #pragma unroll
     for (int r = 0; r < GEMV8_R; ++r) acc[r] = 0.0f;
@@ -578,6 +650,8 @@ __global__ void __launch_bounds__(NT, 2) gemv8_kernel(const GemvParams p) {
     auto consume = [&](const float4 (&w)[GEMV8_R], int it) {
         const int t = it / nsteps, st = it - t * nsteps;
         const int c = st * NT + tid;
+        if (EPI == EPI_RESID && st == 0 && tid < GEMV8_R / 2)
+            xr = gemv_resid_fetch<EPI>(p, (r0 + t * GEMV8_R + 2 * tid < r1) ? r0 + t * GEMV8_R + 2 * tid : p.total_rows);
         if (c < n4) {
             const float4 xv = xs4[c];
 #pragma unroll
@@ -615,7 +689,7 @@ __global__ void __launch_bounds__(NT, 2) gemv8_kernel(const GemvParams p) {
                 s1 += red[par][w8][2 * tid + 1];
             }
             const int v0 = r0 + t * GEMV8_R + 2 * tid;
-            if (v0 < r1) gemv_epilogue_pair<EPI>(p, v0, s0, s1, pos, best);
+            if (v0 < r1) gemv_epilogue_pair<EPI>(p, v0, s0, s1, pos, best, epoch, xr);
         }
 #pragma unroll
         for (int r = 0; r < GEMV8_R; ++r) acc[r] = 0.0f;
@@ -635,7 +709,6 @@ __global__ void __launch_bounds__(NT, 2) gemv8_kernel(const GemvParams p) {
     }
     if (!triggered) pdl_launch_dependents();
     gemv_finish_argmax<EPI>(p, best, &blk_key);
-    gemv_finish_xchg<EPI>(p, (unsigned int)(pair1 - pair0));
 }
 
 // ---- v3: TMA-fed streaming GEMV for bandwidth-bound shapes.
@@ -725,6 +798,20 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
         if (lane == 0) L2B_STAMP(p.trace, 1);
     }
 
+    // the rmsnorm gain is immutable: fetch this thread's slice before waiting on the previous
+    // kernel (on big models it has been evicted from L2 by the weight stream, and after the wait
+    // its DRAM round trip would queue behind this CTA's own ring traffic)
+    constexpr int MAXV = 4;                               // n <= 4 * 320 * 4 = 5120 floats when fused
+    float4 gv[MAXV];
+    if (p.gamma) {
+        const float4 *g4 = reinterpret_cast<const float4 *>(p.gamma);
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const int i = tid + k * TMA_THREADS;
+            gv[k] = (i < n4) ? __ldg(g4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+
     // ---- everything below reads what earlier kernels of this step wrote
     pdl_wait();
     if (p.ctl[CTL_DONE]) {
@@ -738,11 +825,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
     if (p.bump_epoch && blockIdx.x == 0 && tid == 0) const_cast<int *>(p.ctl)[CTL_EPOCH] += 1;
     if (tid == 0) L2B_STAMP(p.trace, 2);
 
-    // stage the activation vector (all threads take part in the barriers of this phase).  Only x
-    // goes through shared memory; the pending residual and the rmsnorm gain are read once,
-    // straight from L2, which keeps the CTA's footprint small enough for the NEXT kernel's CTA
-    // to be co-resident and pre-fill its ring while this one is still streaming.
+    // stage the activation vector (all threads take part in the barriers of this phase)
     {
+        if (p.ll_in) tp_reduce_into_x(p);                 // tensor parallel: x += sum of all ranks' partial rows
         const float *xsrc = p.emb ? p.emb + (size_t)p.ctl[CTL_TOKEN] * p.n : p.x_in;
         if (tid == 0) {
             const uint32_t bytes = (uint32_t)p.n * 4u;
@@ -756,62 +841,15 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
                 rope_s[1][i] = p.rope_sin[(size_t)pos * half + i];
             }
         }
-        // each thread owns the float4 columns tid, tid + 320, ...; fetch its residual slice now
-        constexpr int MAXV = 4;                           // n <= 4 * 320 * 4 = 5120 floats when fused
-        float4 dv[MAXV];
-        const float4 *d4 = reinterpret_cast<const float4 *>(p.delta);
-        const bool have_delta = p.delta || p.xparts;
-        if (p.xparts) {
-            // fused all-reduce, consumer half: wait for every rank's partial rows, sum in rank order
-            if (tid < p.xworld) {
-                const unsigned int want = (unsigned int)p.ctl[CTL_EPOCH] * (unsigned int)p.xcount_per_step;
-                while ((int)(ld_acquire_sys(p.xflags + tid) - want) < 0) { }
-            }
-            __syncthreads();
-            const float4 *pp = reinterpret_cast<const float4 *>(p.xparts);
-#pragma unroll
-            for (int k = 0; k < MAXV; ++k) {
-                const int i = tid + k * TMA_THREADS;
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < n4) {
-                    for (int r = 0; r < p.xworld; ++r) {
-                        const float4 d = __ldcg(pp + (size_t)r * n4 + i);
-                        a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w;
-                    }
-                }
-                dv[k] = a;
-            }
-        } else if (p.delta) {
-#pragma unroll
-            for (int k = 0; k < MAXV; ++k) {
-                const int i = tid + k * TMA_THREADS;
-                dv[k] = (i < n4) ? __ldcg(d4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        // the rmsnorm gain too: it is evicted from L2 by the weight stream on big models, so its
-        // DRAM round trip must overlap the x / residual fetch instead of following the reduction
-        const float4 *g4 = reinterpret_cast<const float4 *>(p.gamma);
-        float4 gv[MAXV];
-        if (p.gamma) {
-#pragma unroll
-            for (int k = 0; k < MAXV; ++k) {
-                const int i = tid + k * TMA_THREADS;
-                gv[k] = (i < n4) ? __ldg(g4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
         mbar_wait(&xbar, 0);
-        if (have_delta || p.gamma || p.x_out) {
+        if (p.gamma || p.x_out) {
             float4 *xs4w = reinterpret_cast<float4 *>(xs);
             float ssq = 0.0f;
 #pragma unroll
             for (int k = 0; k < MAXV; ++k) {
                 const int i = tid + k * TMA_THREADS;
                 if (i < n4) {
-                    float4 v = xs4w[i];
-                    if (have_delta) {
-                        v.x += dv[k].x; v.y += dv[k].y; v.z += dv[k].z; v.w += dv[k].w;   // accum(), :708-713
-                        xs4w[i] = v;
-                    }
+                    const float4 v = xs4w[i];
                     if (p.x_out && blockIdx.x == 0) reinterpret_cast<float4 *>(p.x_out)[i] = v;
                     ssq = fmaf(v.x, v.x, ssq); ssq = fmaf(v.y, v.y, ssq);
                     ssq = fmaf(v.z, v.z, ssq); ssq = fmaf(v.w, v.w, ssq);
@@ -851,34 +889,22 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
             if (p_it == total) pdl_launch_dependents();   // last stage in flight
         }
         if (lane == 0) L2B_STAMP(p.trace, 6);
-        // ---- then warm L2 with the first rows this CTA will stream in the NEXT GEMV kernel
-        if (p.pf_total_rows > 0 && p.pf_bytes > 0) {
-            GemvParams q;
-            q.w0 = p.pf_w0; q.w1 = p.pf_w1; q.w2 = p.pf_w2;
-            q.rows0 = p.pf_rows0; q.rows1 = p.pf_rows1; q.n = p.pf_n;
-            const int npairs_n = (p.pf_total_rows + 1) >> 1;
-            const int base_n = npairs_n / (int)gridDim.x, rem_n = npairs_n % (int)gridDim.x;
-            const int q0 = (b * base_n + min(b, rem_n)) * 2;
-            const int q1 = min((b * base_n + min(b, rem_n) + base_n + (b < rem_n ? 1 : 0)) * 2, p.pf_total_rows);
-            const int row_bytes = p.pf_n * 4;
-            int nrows = (p.pf_bytes + row_bytes - 1) / row_bytes;
-            if (nrows > q1 - q0) nrows = q1 - q0;
-            for (int r = lane; r < nrows; r += 32) {
-                const int v = q0 + r;
-                const float *rp = (p.pf_epi == EPI_QKV)    ? gemv_row_ptr<EPI_QKV>(q, v)
-                                  : (p.pf_epi == EPI_SILU) ? gemv_row_ptr<EPI_SILU>(q, v)
-                                                           : gemv_row_ptr<EPI_STORE>(q, v);
-                prefetch_l2_bulk(rp, (uint32_t)row_bytes);
-            }
-        }
         return;
     }
 
     if (warp == NWARP + 1) {
         // ---- epilogue warp: lanes 0..3 own the four row pairs of each tile
         unsigned long long best = 0ull;
+        const unsigned int epoch = (EPI == EPI_XCHG) ? (unsigned int)p.ctl[CTL_EPOCH] : 0u;
+        // EPI_RESID: the residual values of tile t+1 are fetched while tile t is being reduced
+        float2 xr_next = gemv_resid_fetch<EPI>(p, (lane < GEMV8_R / 2 && r0 + 2 * lane < r1) ? r0 + 2 * lane : p.total_rows);
         for (int t = 0; t < ntiles; ++t) {
             const int par = t & 1, use = t >> 1;
+            const float2 xr = xr_next;
+            {
+                const int vn = r0 + (t + 1) * GEMV8_R + 2 * lane;
+                xr_next = gemv_resid_fetch<EPI>(p, (lane < GEMV8_R / 2 && vn < r1) ? vn : p.total_rows);
+            }
             mbar_wait(&tile_full[par], use & 1);
             float s0 = 0.0f, s1 = 0.0f;
             if (lane < GEMV8_R / 2) {
@@ -902,7 +928,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
                     float *dst = is_q ? p.out0 + i : p.kcache + (size_t)pos * p.kv_dim + i;  // :355,:357
                     *reinterpret_cast<float2 *>(dst) = make_float2(q0, q1);
                 } else {
-                    gemv_epilogue_pair<EPI>(p, vp, s0, s1, pos, best);
+                    gemv_epilogue_pair<EPI>(p, vp, s0, s1, pos, best, epoch, xr);
                 }
             }
         }
@@ -913,12 +939,6 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
                 best = other > best ? other : best;
             }
             if (lane == 0 && best) atomicMax(p.amax, best);
-        }
-        if (EPI == EPI_XCHG) {
-            // all partial rows of this CTA are on their way: publish (system-scope release)
-            __threadfence_system();
-            __syncwarp();
-            if (lane < p.xworld && pair1 > pair0) red_release_sys_add(p.xflag_peer[lane], (unsigned int)(pair1 - pair0));
         }
         if (lane == 0) L2B_STAMP(p.trace, 7);
         return;
@@ -1319,27 +1339,53 @@ __global__ void __launch_bounds__(NT) attention_flash_kernel(const AttnParams p)
 // ---------------------------------------------------------------------------------------
 // Small kernels
 // ---------------------------------------------------------------------------------------
-__global__ void set_ctl_kernel(int *ctl, int token, int pos, int stop_on_bos,
-                               unsigned long long *amax) {
-    ctl[CTL_TOKEN] = token;
-    ctl[CTL_POS] = pos;
-    ctl[CTL_DONE] = 0;
-    ctl[CTL_STEP] = 0;
-    ctl[CTL_STOP_ON_BOS] = stop_on_bos;
-    *amax = 0ull;
-}
-
 // End of one step of the on-device temperature-0 loop (src/main.zig:999-1041):
 // choose next = forced[step] or argmax, record it, stop on BOS, advance (token, pos).
-__global__ void advance_kernel(int *ctl, unsigned long long *amax, const int *forced, int *out_next,
-                               int *n_done) {
+// Tensor parallel (world > 1): every rank first sends its local packed maximum to every rank as
+// two LL units and takes the maximum of all of them, so all ranks advance with the same token
+// without a collective launch.
+struct AdvanceParams {
+    int *ctl;
+    unsigned long long *amax;
+    const int *forced;
+    int *out_next, *n_done;
+    int world, rank;
+    unsigned long long *ll_out[MAX_TP];   // rank d's landing area for my key: 2 units
+    const unsigned long long *ll_in;      // my landing area: [world][2] units
+    unsigned long long spin_ns;
+};
+__global__ void advance_kernel(const AdvanceParams p) {
+    pdl_wait();
+    int *ctl = p.ctl;
     if (ctl[CTL_DONE]) return;
+    const int tid = threadIdx.x;
+    __shared__ unsigned long long keys[MAX_TP];
+    unsigned long long key = *p.amax;
+    if (p.world > 1) {
+        const unsigned int epoch = (unsigned int)ctl[CTL_EPOCH];
+        if (tid < p.world)
+            ll_store2(p.ll_out[tid], __uint_as_float((unsigned int)(key >> 32)),
+                      __uint_as_float((unsigned int)(key & 0xFFFFFFFFull)), epoch);
+        if (tid < p.world) {
+            SpinGuard sg = spin_guard(ctl, p.spin_ns);
+            uint4 a = ll_load2(p.ll_in + 2 * tid);
+            while (a.y != epoch || a.w != epoch) {
+                if (sg.expired()) break;
+                a = ll_load2(p.ll_in + 2 * tid);
+            }
+            keys[tid] = ((unsigned long long)a.x << 32) | (unsigned long long)a.z;
+        }
+        __syncthreads();
+        if (tid == 0)
+            for (int r = 0; r < p.world; ++r) key = keys[r] > key ? keys[r] : key;
+    }
+    if (tid != 0) return;
     const int step = ctl[CTL_STEP];
-    int next = (int)(0xFFFFFFFFu - (unsigned int)(*amax & 0xFFFFFFFFull));
-    if (forced && forced[step] >= 0) next = forced[step];
-    out_next[step] = next;
-    *n_done = step + 1;
-    *amax = 0ull;
+    int next = (int)(0xFFFFFFFFu - (unsigned int)(key & 0xFFFFFFFFull));
+    if (p.forced && p.forced[step] >= 0) next = p.forced[step];
+    p.out_next[step] = next;
+    *p.n_done = step + 1;
+    *p.amax = 0ull;
     if (ctl[CTL_STOP_ON_BOS] && next == 1) {   // :1017-1019
         ctl[CTL_DONE] = 1;
         return;
@@ -1347,6 +1393,119 @@ __global__ void advance_kernel(int *ctl, unsigned long long *amax, const int *fo
     ctl[CTL_TOKEN] = next;
     ctl[CTL_POS] = ctl[CTL_POS] + 1;
     ctl[CTL_STEP] = step + 1;
+}
+
+// Tensor parallel logits: every rank's classifier sent its vocab slice as LL units (EPI_XCHG with
+// row_base = rank * vocab_loc); this kernel waits for all of them and writes the dense logits
+// vector the D2H copy (and the sampler) read.  No collective launch per token.
+__global__ void __launch_bounds__(NT) gather_logits_kernel(float *logits, const unsigned long long *ll_in,
+                                                           int vocab, const int *ctl, unsigned long long spin_ns) {
+    pdl_wait();
+    if (ctl[CTL_DONE]) return;
+    const unsigned int epoch = (unsigned int)ctl[CTL_EPOCH];
+    SpinGuard sg = spin_guard(ctl, spin_ns);
+    const int npairs = vocab >> 1;                          // vocab / world is even (checked at create)
+    for (int i = blockIdx.x * NT + threadIdx.x; i < npairs; i += gridDim.x * NT) {
+        uint4 a = ll_load2(ll_in + 2 * (size_t)i);
+        while (a.y != epoch || a.w != epoch) {
+            if (sg.expired()) break;
+            a = ll_load2(ll_in + 2 * (size_t)i);
+        }
+        reinterpret_cast<float2 *>(logits)[i] = make_float2(__uint_as_float(a.x), __uint_as_float(a.z));
+    }
+}
+
+// NCCL baseline mode (L2B_TP=nccl) only: x += all-reduced delta, the residual add of :395/:422
+__global__ void __launch_bounds__(NT) resid_add_kernel(float *x, const float *delta, int n, const int *ctl) {
+    if (ctl[CTL_DONE]) return;
+    for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT) x[i] += delta[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// Sampler preparation on the device (src/main.zig:1005-1012, :752-768), SURVEY 8f.1: the part of
+// temperature sampling that touches all vocab_size logits.  One CTA:
+//   logits /= temperature (:1006); softmax in place (:1008, :687-706: max, exp, sum, divide);
+//   top-p prefilter (:761-768): candidates with prob >= (1-p)/(n-1), compacted IN INDEX ORDER.
+// The random draw, the sort of the (few) candidates and the CDF walk stay on the host because they
+// use the host's PRNG (:730, :788).  temperature / top-p come from ctl[CTL_TEMP] / ctl[CTL_TOPP].
+// ---------------------------------------------------------------------------------------
+constexpr int SAMP_THREADS = 1024;
+struct ProbIndex { float prob; int index; };
+__global__ void __launch_bounds__(SAMP_THREADS) sample_prep_kernel(float *logits, int n, const int *ctl,
+                                                                   ProbIndex *cand, int cand_cap, int *n_cand) {
+    pdl_wait();
+    if (ctl[CTL_DONE]) return;
+    __shared__ float red[SAMP_THREADS / 32 + 1];
+    __shared__ int wsum[SAMP_THREADS / 32 + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float temp = __int_as_float(ctl[CTL_TEMP]);
+    const float top_p = __int_as_float(ctl[CTL_TOPP]);
+    // pass 1: scaled logits and their maximum
+    float m = -INFINITY;
+    for (int i = tid; i < n; i += SAMP_THREADS) {
+        const float v = __fdiv_rn(logits[i], temp);         // :1006
+        logits[i] = v;
+        m = fmaxf(m, v);
+    }
+    m = warp_max(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[lane];                                           // 32 warps
+    m = warp_max(m);
+    __syncthreads();
+    // pass 2: exp and sum
+    float l = 0.0f;
+    for (int i = tid; i < n; i += SAMP_THREADS) {
+        const float e = expf(logits[i] - m);                 // :699
+        logits[i] = e;
+        l += e;
+    }
+    l = warp_sum(l);
+    if (lane == 0) red[warp] = l;
+    __syncthreads();
+    l = red[lane];
+    l = warp_sum(l);
+    __syncthreads();
+    // pass 3: normalise (:703-705) and select candidates; thread t owns a CONTIGUOUS index range so
+    // that an exclusive scan of the per-thread counts yields index-ordered compaction
+    const int per = (n + SAMP_THREADS - 1) / SAMP_THREADS;
+    const int i0 = tid * per, i1 = min(n, i0 + per);
+    const float cutoff = __fdiv_rn(1.0f - top_p, (float)n - 1.0f);   // :761
+    int cnt = 0;
+    for (int i = i0; i < i1; ++i) {
+        const float pr = __fdiv_rn(logits[i], l);
+        logits[i] = pr;
+        if (top_p >= 0.0f && pr >= cutoff) ++cnt;            // :764
+    }
+    if (top_p < 0.0f) { if (tid == 0) *n_cand = -1; return; }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = wsum[lane];
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        wsum[lane] = wi - w;                                 // exclusive prefix of the warp totals
+        if (lane == 31) *n_cand = wi;
+    }
+    __syncthreads();
+    int off = wsum[warp] + incl - cnt;
+    for (int i = i0; i < i1; ++i) {
+        const float pr = logits[i];
+        if (pr >= cutoff) {
+            if (off < cand_cap) { cand[off].prob = pr; cand[off].index = i; }
+            ++off;
+        }
+    }
 }
 
 // standalone rmsnorm (unit-test surface; the hot path fuses it into the GEMV prologue)

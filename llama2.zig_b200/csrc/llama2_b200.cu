@@ -2,39 +2,49 @@
 //
 // Replaces transformer() of the reference (src/main.zig:285-430) and the device-side
 // equivalents of Weights.init (:73-115) / RunState.init (:137-154).  Pure CUDA runtime:
-// no torch, no CPU fallback.  One context = one GPU = one stream; a decode step is a CUDA
-// graph of 5 kernels per layer + classifier, replayed per token.
+// no torch, no CPU fallback.  One rank = one GPU = one stream; a decode step is a CUDA graph
+// of 5 kernels per layer + classifier, replayed per token.  A context is either one rank
+// (single GPU, or one process per GPU with peers reached through CUDA IPC) or a group of ranks
+// inside one process (l2b_create with n_gpus > 1: peers reached through UVA peer access).
 #include "../../include/llama2_b200.h"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
-#include <nccl.h>   // types only; the library is dlopen()ed on first multi-GPU use
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
+#include <set>
 #include <string>
 #include <vector>
 
 #include "l2b_device.cuh"
-#include "l2b_mega.cuh"
 
 using namespace l2b;
 
 // ---------------------------------------------------------------------------------------
-// NCCL through dlopen: single-GPU use never needs libnccl to be present.
+// NCCL through dlopen: single-GPU use never needs libnccl (or its headers) to be present.  NCCL
+// is only the bootstrap of the one-process-per-GPU mode (it carries the CUDA IPC handles at
+// create time) and the data plane of the L2B_TP=nccl baseline; the default data plane is this
+// library's own peer-memory exchange.  The few types / enum values used are restated here.
 // ---------------------------------------------------------------------------------------
 namespace {
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+constexpr int ncclSuccess = 0;
+constexpr int ncclChar = 0, ncclInt = 2, ncclUint64 = 5, ncclFloat = 7;   // ncclDataType_t
+constexpr int ncclSum = 0, ncclMax = 2;                                   // ncclRedOp_t
+
 struct NcclApi {
     void *handle = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
-                              cudaStream_t) = nullptr;
-    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t,
-                              cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -70,11 +80,18 @@ bool nccl_load(std::string *err) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
-// Context
+// Context (one rank)
 // ---------------------------------------------------------------------------------------
+enum StepMode { MODE_LOGITS = 0, MODE_ARGMAX = 1, MODE_SAMPLE = 2 };
+enum GraphId { G_LOGITS = 0, G_ARGMAX_ONE = 1, G_ARGMAX_LOOP = 2, G_SAMPLE = 3, G_COUNT = 4 };
+constexpr int kCandCap = 8192;               // top-p candidates returned per step (more => host filters itself)
+
 struct l2b_ctx {
     l2b_config cfg{};
     int rank = 0, world = 1, device = 0, num_sms = 0;
+    // in-process group (l2b_create with n_gpus > 1): the leader (rank 0) owns the other ranks
+    std::vector<l2b_ctx *> members;          // leader only: all ranks, [0] == this
+    l2b_ctx *leader = nullptr;
     // derived sizes (local = this rank's shard)
     int dim = 0, hidden = 0, head_size = 0, kv_mul = 0;
     int q_dim = 0, kv_dim = 0;              // global
@@ -83,10 +100,9 @@ struct l2b_ctx {
     float *emb = nullptr, *rms_att = nullptr, *rms_ffn = nullptr, *rms_final = nullptr;
     float *wq = nullptr, *wk = nullptr, *wv = nullptr, *wo = nullptr;
     float *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *wcls = nullptr;
-    bool wcls_owned = false;
     // device run state (RunState, :119-135)
-    float *X[2] = {nullptr, nullptr};       // residual stream, ping-pong
-    float *delta_a = nullptr, *delta_f = nullptr;  // pending residual from wo / w2 (all-reduced in TP)
+    float *X = nullptr;                      // residual stream x; wo / w2 add into it (:395, :422)
+    float *delta = nullptr;                  // L2B_TP=nccl baseline only: partial rows before the NCCL all-reduce
     float *q = nullptr, *xb = nullptr, *hb = nullptr, *logits = nullptr, *logits_loc = nullptr;
     float *kcache = nullptr, *vcache = nullptr;     // (L, seq_len, kv_loc)
     float *rope_cos = nullptr, *rope_sin = nullptr; // (seq_len, head_size/2)
@@ -95,48 +111,60 @@ struct l2b_ctx {
     int *ctl = nullptr;
     unsigned long long *amax = nullptr;
     int *gen_forced = nullptr, *gen_out = nullptr, *gen_ndone = nullptr;
-    int final_x = 0;                        // which X[] holds x after the step
+    ProbIndex *cand = nullptr;               // sampler: top-p candidates (index order)
+    int *n_cand = nullptr;
     // host pinned
-    float *h_logits = nullptr;
-    int *h_ints = nullptr;                  // [0]=next, [1]=n_done
-    int *h_gen = nullptr;                   // seq_len ints
+    float *h_logits = nullptr;               // vocab floats: logits, or probabilities after sample_prep
+    int *h_ctl = nullptr;                    // [0..7] host -> device control words, [8..15] device -> host status
+    int *h_ints = nullptr;                   // [0]=next, [1]=n_done, [2]=n_cand
+    int *h_gen = nullptr;                    // seq_len ints
+    ProbIndex *h_cand = nullptr;
     // attention launch shape
-    int nsplit = 1, min_chunk = 256, attn_smem = 0;   // timeline splits of >= 256 positions (A/B: 64 -> 256 = +14% on stories15M)
+    int nsplit = 1, min_chunk = 256, attn_smem = 0;   // timeline splits of >= 256 positions
     // streams / graphs
     cudaStream_t stream = nullptr;
-    cudaGraphExec_t graph_logits = nullptr, graph_argmax = nullptr;
+    cudaGraphExec_t graphs[G_COUNT] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool use_graphs = true;
     bool use_pdl = true;
-    bool use_mega = false;                   // one persistent cooperative kernel per step
-    unsigned long long *gbar = nullptr;      // its grid-barrier counter
-    int mega_nstage = 0, mega_xs_floats = 0, mega_smem = 0;
     int last_grid = 0;                       // grid of the most recent GEMV launch
-    // fused all-reduce over peer memory (world > 1): exchange buffer [slots][world][dim] + counters
+    // tensor-parallel exchange over peer memory (world > 1).  One arena per rank holds every landing
+    // area, so one IPC handle (or one UVA pointer) per rank is all the ranks trade at create time:
+    //   ll_red    [2L reduce points][world source ranks][dim] LL units   (wo / w2 partial rows)
+    //   ll_logits [vocab] LL units                                       (classifier slices of all ranks)
+    //   ll_amax   [world][2] LL units                                    (packed argmax keys)
+    //   rdone     [2L] slice counters (local use only)
     bool use_p2p = false;
-    float *xchg = nullptr;
-    unsigned int *xflags = nullptr;
-    float *peer_xchg[MAX_TP] = {};
-    unsigned int *peer_flags[MAX_TP] = {};
+    unsigned char *arena = nullptr;
+    size_t arena_bytes = 0, off_red = 0, off_logits = 0, off_amax = 0, off_rdone = 0;
+    unsigned char *peer_arena[MAX_TP] = {};
     std::vector<void *> ipc_opened;
-    std::vector<int> xgrid;                  // producer CTAs per reduce point (same on every rank)
+    unsigned long long spin_ns = 20ull * 1000000000ull;   // bound on every peer wait (L2B_SPIN_TIMEOUT_MS)
     bool attn_flash = true;                  // flash-decoding attention (false: 3-pass kernel)
     unsigned long long *trace = nullptr;     // L2B_TRACE=1: [launch][TRACE_MAX_CTAS][TRACE_SLOTS] timeline
     int trace_launches = 0;
-    int pf_bytes = 0;                        // per-CTA L2 prefetch of the next GEMV's first rows (L2B_PF_KB; measured: no gain)
-    int tma_ctas_per_sm = 1;                 // CTAs of ONE TMA kernel per SM (the other half-SM is for its successor)
-    int tma_stages = 0;                      // 0 = auto (two CTAs per SM); else forced ring depth
+    int tma_ctas_per_sm = 1;
+    int tma_stages = 0;                      // 0 = auto; else forced ring depth
     bool big_kernel_tma = true;              // bandwidth-bound GEMVs: TMA-ring kernel (false: register-fed 8-row kernel)
-    long long gemv8_min_bytes = 8ll << 20;   // >= this many weight bytes (and n >= 1024): 8-row kernel; -1 = never
+    long long gemv8_min_bytes = 8ll << 20;   // >= this many weight bytes (and n >= 512): streaming kernel; -1 = never
+    int force_kernel = 0;                    // l2b_op_fused_matmul: 0 auto, 1 small, 2 register-fed 8-row, 3 TMA ring
     int launches_per_step = 0;
-    // comm
+    std::set<const void *> attr_done;        // kernels whose max-dynamic-smem attribute is set on this device
+    // comm (bootstrap / nccl baseline)
     ncclComm_t comm = nullptr;
     // bookkeeping
     int n_appended = 0;
     float last_ms = 0.0f;
     int last_launches = 0;
+    double load_ms = 0.0;                    // checkpoint upload wall time (l2b_load_stats)
+    uint64_t load_bytes = 0;
     std::string err;
     std::vector<void *> owned;              // device allocations to free
+    // upload staging (pinned, double-buffered)
+    unsigned char *stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    int stage_next = 0;
     // per-kernel profiling (l2b_profile_step)
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -178,6 +206,12 @@ int fail(l2b_ctx *ctx, int code, const char *msg) {
     return code;
 }
 
+// all ranks this handle drives from this process (1 unless it is an in-process group)
+std::vector<l2b_ctx *> locals(l2b_ctx *ctx) {
+    if (!ctx->members.empty()) return ctx->members;
+    return std::vector<l2b_ctx *>{ctx};
+}
+
 template <typename T>
 int dev_alloc(l2b_ctx *ctx, T **p, size_t count) {
     void *q = nullptr;
@@ -200,11 +234,13 @@ int validate_config(const l2b_config *c, int world, std::string *why) {
     const int hs = c->dim / c->n_heads;
     if (c->dim % 4 || c->hidden_dim % 4) return bad("dim and hidden_dim must be multiples of 4");
     if (hs % 4) return bad("head_size must be a multiple of 4");
-    if (hs / 4 > NT) return bad("head_size too large");
+    // the attention kernels write one output element per thread (NT = 256) and the RoPE row of a
+    // position is staged as head_size/2 <= 128 pairs
+    if (hs > NT) return bad("head_size > 256 is not supported");
     if (world != 1 && world != 2 && world != 4 && world != 8) return bad("world_size must be 1, 2, 4 or 8");
     if (c->n_kv_heads % world) return bad("n_kv_heads % world_size != 0");
     if ((c->hidden_dim / world) % 4 || c->hidden_dim % world) return bad("hidden_dim/world_size must be a multiple of 4");
-    if (c->vocab_size % world) return bad("vocab_size % world_size != 0");
+    if (c->vocab_size % world || (world > 1 && (c->vocab_size / world) % 2)) return bad("vocab_size/world_size must be an even integer");
     return L2B_OK;
 }
 
@@ -227,6 +263,52 @@ struct Source {
     uint64_t seed = 0;
 };
 
+// Checkpoint ingest (the reference slurps the file into pageable heap memory,
+// src/main.zig:955-964).  The caller's buffer is pageable, so a plain cudaMemcpy would bounce every
+// byte through the driver's small internal staging buffer synchronously.  Here the payload moves
+// in chunks through two pinned buffers: while chunk k is in flight on the copy engine, the host
+// is already filling the other buffer with chunk k+1 (for column-sharded tensors the host-side
+// fill also compacts the strided window, so the DMA is always a dense 1-D copy).
+int upload(l2b_ctx *ctx, float *dst, const float *src, uint64_t rows, uint64_t cols, uint64_t src_pitch) {
+    if (!ctx->stage[0]) {
+        size_t want = 32ull << 20;
+        const char *env = getenv("L2B_STAGE_MB");
+        if (env && atoi(env) > 0) want = (size_t)atoi(env) << 20;
+        ctx->stage_bytes = want;
+        for (int i = 0; i < 2; ++i) {
+            L2B_CUDA(ctx, cudaHostAlloc((void **)&ctx->stage[i], want, cudaHostAllocDefault));
+            L2B_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+        }
+    }
+    const uint64_t row_bytes = cols * sizeof(float);
+    const bool dense = (src_pitch == cols);
+    const uint64_t total = rows * row_bytes;
+    uint64_t done = 0;                       // bytes of the dense destination already issued
+    while (done < total) {
+        const int b = ctx->stage_next;
+        ctx->stage_next ^= 1;
+        L2B_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[b]));   // previous DMA out of this buffer finished
+        uint64_t chunk = total - done < ctx->stage_bytes ? total - done : ctx->stage_bytes;
+        if (!dense) {
+            // whole rows only (a chunk never splits a row of a sharded window)
+            uint64_t r = chunk / row_bytes;
+            if (r == 0) return fail(ctx, L2B_ERR_UNSUPPORTED, "row larger than the upload staging buffer");
+            chunk = r * row_bytes;
+            const uint64_t row0 = done / row_bytes;
+            for (uint64_t i = 0; i < r; ++i)
+                memcpy(ctx->stage[b] + i * row_bytes, src + (row0 + i) * src_pitch, row_bytes);
+        } else {
+            memcpy(ctx->stage[b], reinterpret_cast<const unsigned char *>(src) + done, chunk);
+        }
+        L2B_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<unsigned char *>(dst) + done, ctx->stage[b], chunk,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        L2B_CUDA(ctx, cudaEventRecord(ctx->stage_ev[b], ctx->stream));
+        done += chunk;
+    }
+    ctx->load_bytes += total;
+    return L2B_OK;
+}
+
 int materialize(l2b_ctx *ctx, float **dptr, const Source &src, uint64_t payload_off, int tensor_id,
                 uint64_t L, uint64_t rows, uint64_t cols, ShardMode mode, Dist dist) {
     const uint64_t g = ctx->world, r = ctx->rank;
@@ -243,13 +325,9 @@ int materialize(l2b_ctx *ctx, float **dptr, const Source &src, uint64_t payload_
     for (uint64_t l = 0; l < nl; ++l) {
         float *dst = *dptr + l * rows_loc * cols_loc;
         const uint64_t first = l * rows * cols + row0 * cols + col0;
-        if (src.host && whole) {
-            L2B_CUDA(ctx, cudaMemcpy(dst, src.host + payload_off, L * rows * cols * sizeof(float),
-                                     cudaMemcpyHostToDevice));
-        } else if (src.host) {
-            L2B_CUDA(ctx, cudaMemcpy2D(dst, cols_loc * sizeof(float), src.host + payload_off + first,
-                                       cols * sizeof(float), cols_loc * sizeof(float), rr,
-                                       cudaMemcpyHostToDevice));
+        if (src.host) {
+            rc = upload(ctx, dst, src.host + payload_off + first, rr, cols_loc, cols);
+            if (rc) return rc;
         } else {
             const uint64_t total = rr * cols_loc;
             int blocks = (int)((total + 255) / 256 < (uint64_t)(ctx->num_sms * 16)
@@ -282,6 +360,7 @@ gemv_fn gemv_pick(int tpr) {
 gemv_fn gemv_pick(int epi, int tpr) {
     switch (epi) {
     case EPI_XCHG: return gemv_pick<EPI_XCHG>(tpr);
+    case EPI_RESID: return gemv_pick<EPI_RESID>(tpr);
     case EPI_STORE: return gemv_pick<EPI_STORE>(tpr);
     case EPI_ARGMAX: return gemv_pick<EPI_ARGMAX>(tpr);
     case EPI_QKV: return gemv_pick<EPI_QKV>(tpr);
@@ -316,6 +395,7 @@ int prof_mark(l2b_ctx *ctx, const char *name, int layer, uint64_t bytes, cudaStr
 gemv_fn gemv_tma_pick(int epi) {
     switch (epi) {
     case EPI_XCHG: return gemv_tma_kernel<EPI_XCHG>;
+    case EPI_RESID: return gemv_tma_kernel<EPI_RESID>;
     case EPI_STORE: return gemv_tma_kernel<EPI_STORE>;
     case EPI_ARGMAX: return gemv_tma_kernel<EPI_ARGMAX>;
     case EPI_QKV: return gemv_tma_kernel<EPI_QKV>;
@@ -326,11 +406,24 @@ gemv_fn gemv_tma_pick(int epi) {
 gemv_fn gemv8_pick(int epi) {
     switch (epi) {
     case EPI_XCHG: return gemv8_kernel<EPI_XCHG>;
+    case EPI_RESID: return gemv8_kernel<EPI_RESID>;
     case EPI_STORE: return gemv8_kernel<EPI_STORE>;
     case EPI_ARGMAX: return gemv8_kernel<EPI_ARGMAX>;
     case EPI_QKV: return gemv8_kernel<EPI_QKV>;
     default: return gemv8_kernel<EPI_SILU>;
     }
+}
+
+cudaLaunchAttribute pdl_attr() {
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    return at;
+}
+
+unsigned long long *trace_slot(l2b_ctx *ctx) {
+    if (!ctx->trace || ctx->profiling) return nullptr;
+    return ctx->trace + (size_t)(ctx->last_launches % ctx->trace_launches) * TRACE_MAX_CTAS * TRACE_SLOTS;
 }
 
 int launch_gemv(l2b_ctx *ctx, int epi, const GemvParams &p, cudaStream_t st, const char *name = "gemv",
@@ -339,11 +432,13 @@ int launch_gemv(l2b_ctx *ctx, int epi, const GemvParams &p, cudaStream_t st, con
         int prc = prof_mark(ctx, name, layer, (uint64_t)p.total_rows * p.n * 4ull, st);
         if (prc) return prc;
     }
-    const size_t xbytes = (size_t)p.n * 4 * (1 + (p.delta ? 1 : 0) + (p.gamma ? 1 : 0));
+    const size_t xbytes = (size_t)p.n * 4 * (1 + (p.gamma ? 1 : 0));
     // bandwidth-bound shapes take the TMA-ring kernel (or the register-fed 8-row kernel when
     // L2B_GEMV_BIG=ldg), latency-bound ones the fine-grained kernel
-    const bool big = ctx->gemv8_min_bytes >= 0 && p.n >= 1024 &&
-                     (uint64_t)p.total_rows * p.n * 4ull >= (uint64_t)ctx->gemv8_min_bytes;
+    bool big = ctx->gemv8_min_bytes >= 0 && p.n >= 512 &&
+               (uint64_t)p.total_rows * p.n * 4ull >= (uint64_t)ctx->gemv8_min_bytes;
+    if (ctx->force_kernel == 1) big = false;
+    if (ctx->force_kernel >= 2) big = true;
     // TMA-ring kernel: only x is staged in shared memory, the rest of the SM's 227 KB is the ring
     // (measured: 5-6 stages of 32 KB on ONE CTA per SM beat 2 x 3 stages and beat leaving half
     // the SM to the successor kernel's pre-fill; profiles/r01_tma_ring_variants.md)
@@ -351,18 +446,18 @@ int launch_gemv(l2b_ctx *ctx, int epi, const GemvParams &p, cudaStream_t st, con
     const size_t xonly = (size_t)p.n * 4;
     int nstage = ctx->tma_stages > 0 ? ctx->tma_stages : (int)(((size_t)kMaxSmemOptin - xonly) / stage_bytes);
     if (nstage > TMA_MAX_STAGES) nstage = TMA_MAX_STAGES;
-    const bool fused_ok = !(p.delta || p.gamma || p.xparts) || p.n <= 4 * TMA_THREADS * 4;   // register slices of delta/gamma
-    const bool tma = big && ctx->big_kernel_tma && nstage >= 2 && fused_ok && p.head_size <= 256 &&
-                     (size_t)nstage * stage_bytes + xonly <= (size_t)kMaxSmemOptin;
+    const bool fused_ok = !p.gamma || p.n <= 4 * TMA_THREADS * 4;   // register slices of the rmsnorm gain
+    bool tma = big && ctx->big_kernel_tma && nstage >= 2 && fused_ok && p.head_size <= 256 &&
+               (size_t)nstage * stage_bytes + xonly <= (size_t)kMaxSmemOptin;
+    if (ctx->force_kernel == 2) tma = false;
+    if (ctx->force_kernel == 3 && !tma) return fail(ctx, L2B_ERR_UNSUPPORTED, "shape does not fit the TMA-ring kernel");
     const size_t smem = tma ? (size_t)nstage * stage_bytes + xonly : xbytes;
     if (smem > (size_t)kMaxSmemOptin) return fail(ctx, L2B_ERR_UNSUPPORTED, "activation vector too large for shared memory");
     const int tpr = gemv_tpr(p.n);
     gemv_fn fn = tma ? gemv_tma_pick(epi) : big ? gemv8_pick(epi) : gemv_pick(epi, tpr);
-    static bool attr_done[5][8][16] = {};
-    const int ti = tma ? 7 : big ? 6 : tpr == 8 ? 0 : tpr == 16 ? 1 : tpr == 32 ? 2 : tpr == 64 ? 3 : tpr == 128 ? 4 : 5;
-    if (!attr_done[epi][ti][ctx->device & 15]) {
+    if (!ctx->attr_done.count((const void *)fn)) {
         L2B_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
-        attr_done[epi][ti][ctx->device & 15] = true;
+        ctx->attr_done.insert((const void *)fn);
     }
     const int threads = tma ? TMA_THREADS : NT;
     int occ = 0;
@@ -384,14 +479,13 @@ int launch_gemv(l2b_ctx *ctx, int epi, const GemvParams &p, cudaStream_t st, con
     lc.blockDim = dim3(threads);
     lc.dynamicSmemBytes = smem;
     lc.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[1] = {pdl_attr()};
     lc.attrs = at;
     lc.numAttrs = ctx->use_pdl ? 1 : 0;
     GemvParams pp = p;
     pp.nstage = nstage;
-    pp.trace = (ctx->trace && !ctx->profiling) ? ctx->trace + (size_t)(ctx->last_launches % ctx->trace_launches) * TRACE_MAX_CTAS * TRACE_SLOTS : nullptr;
+    pp.spin_ns = ctx->spin_ns;
+    pp.trace = trace_slot(ctx);
     ctx->last_grid = grid;
     L2B_CUDA(ctx, cudaLaunchKernelEx(&lc, fn, pp));
     ++ctx->last_launches;
@@ -425,8 +519,7 @@ attn_fn pick_attention(int head_size, bool flash, size_t *smem) {
 
 int launch_attention(l2b_ctx *ctx, int layer, cudaStream_t st) {
     if (ctx->profiling) {
-        int hpos = 0;   // the host knows pos only through the last set_ctl; stored in n_appended-1
-        hpos = ctx->n_appended > 0 ? ctx->n_appended - 1 : 0;
+        const int hpos = ctx->n_appended > 0 ? ctx->n_appended - 1 : 0;
         int prc = prof_mark(ctx, "attention", layer, 2ull * (uint64_t)(hpos + 1) * ctx->kv_loc * 4ull, st);
         if (prc) return prc;
     }
@@ -445,7 +538,7 @@ int launch_attention(l2b_ctx *ctx, int layer, cudaStream_t st) {
     a.kv_mul = ctx->kv_mul;
     a.nsplit = ctx->nsplit;
     a.min_chunk = ctx->min_chunk;
-    a.trace = (ctx->trace && !ctx->profiling) ? ctx->trace + (size_t)(ctx->last_launches % ctx->trace_launches) * TRACE_MAX_CTAS * TRACE_SLOTS : nullptr;
+    a.trace = trace_slot(ctx);
     size_t smem = ctx->attn_smem;
     attn_fn fn = pick_attention(ctx->head_size, ctx->attn_flash, &smem);
     cudaLaunchConfig_t lc{};
@@ -453,9 +546,7 @@ int launch_attention(l2b_ctx *ctx, int layer, cudaStream_t st) {
     lc.blockDim = dim3(NT);
     lc.dynamicSmemBytes = smem;
     lc.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[1] = {pdl_attr()};
     lc.attrs = at;
     lc.numAttrs = ctx->use_pdl ? 1 : 0;
     L2B_CUDA(ctx, cudaLaunchKernelEx(&lc, fn, a));
@@ -463,54 +554,102 @@ int launch_attention(l2b_ctx *ctx, int layer, cudaStream_t st) {
     return L2B_OK;
 }
 
-// One decode step on `st` (transformer(), src/main.zig:285-430).  want_argmax selects the
-// classifier epilogue.  All (token, pos) dependence is through ctx->ctl, so the sequence is
-// capturable once and replayed.
-int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
+// ---- tensor-parallel landing areas (offsets into an arena; same layout on every rank) --------
+unsigned long long *ll_red_at(unsigned char *arena, const l2b_ctx *c, int slot, int src_rank) {
+    return reinterpret_cast<unsigned long long *>(arena + c->off_red) + ((size_t)slot * c->world + src_rank) * c->dim;
+}
+unsigned long long *ll_logits_at(unsigned char *arena, const l2b_ctx *c) {
+    return reinterpret_cast<unsigned long long *>(arena + c->off_logits);
+}
+unsigned long long *ll_amax_at(unsigned char *arena, const l2b_ctx *c, int src_rank) {
+    return reinterpret_cast<unsigned long long *>(arena + c->off_amax) + 2 * (size_t)src_rank;
+}
+unsigned int *rdone_at(const l2b_ctx *c, int slot) {
+    return reinterpret_cast<unsigned int *>(c->arena + c->off_rdone) + slot;
+}
+
+int launch_small(l2b_ctx *ctx, const void *fn, dim3 grid, dim3 block, void **args, cudaStream_t st, bool pdl) {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = grid;
+    lc.blockDim = block;
+    lc.stream = st;
+    cudaLaunchAttribute at[1] = {pdl_attr()};
+    lc.attrs = at;
+    lc.numAttrs = (pdl && ctx->use_pdl) ? 1 : 0;
+    L2B_CUDA(ctx, cudaLaunchKernelExC(&lc, fn, args));
+    ++ctx->last_launches;
+    return L2B_OK;
+}
+
+int launch_advance(l2b_ctx *ctx, cudaStream_t st, bool forced, bool exchange) {
+    AdvanceParams a{};
+    a.ctl = ctx->ctl;
+    a.amax = ctx->amax;
+    a.forced = forced ? ctx->gen_forced : nullptr;
+    a.out_next = ctx->gen_out;
+    a.n_done = ctx->gen_ndone;
+    a.world = exchange ? ctx->world : 1;
+    a.rank = ctx->rank;
+    a.spin_ns = ctx->spin_ns;
+    if (exchange) {
+        for (int r = 0; r < ctx->world; ++r) a.ll_out[r] = ll_amax_at(ctx->peer_arena[r], ctx, ctx->rank);
+        a.ll_in = ll_amax_at(ctx->arena, ctx, 0);
+    }
+    void *args[] = {&a};
+    return launch_small(ctx, (const void *)advance_kernel, dim3(1), dim3(32), args, st, true);
+}
+
+// One decode step on `st` (transformer(), src/main.zig:285-430).  All (token, pos) dependence is
+// through ctx->ctl, so the sequence is capturable once and replayed.
+int enqueue_step(l2b_ctx *ctx, cudaStream_t st, StepMode mode) {
     const l2b_config &c = ctx->cfg;
     const int dim = ctx->dim;
-    int cur = 0;
-    // weight map of the GEMV that follows a kernel, for its L2 prefetch (see GemvParams::pf_*)
-    auto set_pf = [&](GemvParams &g, int epi, const float *w0, const float *w1, const float *w2, int rows0,
-                      int rows1, int total, int n) {
-        g.pf_epi = epi; g.pf_w0 = w0; g.pf_w1 = w1; g.pf_w2 = w2;
-        g.pf_rows0 = rows0; g.pf_rows1 = rows1; g.pf_total_rows = total; g.pf_n = n;
-        g.pf_bytes = ctx->pf_bytes;
+    const bool tp = ctx->world > 1;
+    const bool p2p = tp && ctx->use_p2p;
+    auto consume_slot = [&](GemvParams &g, int slot) {      // x += sum of all ranks' partial rows of `slot`
+        g.ll_in = ll_red_at(ctx->arena, ctx, slot, 0);
+        g.rdone = rdone_at(ctx, slot);
+        g.xworld = ctx->world;
     };
-    auto pf_qkv = [&](GemvParams &g, int l) {
-        set_pf(g, EPI_QKV, ctx->wq + (size_t)l * ctx->q_loc * dim, ctx->wk + (size_t)l * ctx->kv_loc * dim,
-               ctx->wv + (size_t)l * ctx->kv_loc * dim, ctx->q_loc, ctx->kv_loc, ctx->q_loc + 2 * ctx->kv_loc, dim);
+    auto produce_slot = [&](GemvParams &g, int slot) {      // my partial rows go to every rank
+        g.ll_ndst = ctx->world;
+        for (int r = 0; r < ctx->world; ++r) g.ll_out[r] = ll_red_at(ctx->peer_arena[r], ctx, slot, ctx->rank);
+    };
+    // wo / w2: row-parallel GEMV whose result is added to the residual stream (:392-395, :419-422)
+    auto residual_gemv = [&](GemvParams &g, int slot, const char *name, int l) -> int {
+        g.total_rows = dim; g.rows0 = dim;
+        int rc;
+        if (!tp) {
+            g.out0 = ctx->X;
+            rc = launch_gemv(ctx, EPI_RESID, g, st, name, l);
+        } else if (p2p) {
+            produce_slot(g, slot);
+            rc = launch_gemv(ctx, EPI_XCHG, g, st, name, l);
+        } else {
+            g.out0 = ctx->delta;
+            rc = launch_gemv(ctx, EPI_STORE, g, st, name, l);
+            if (rc) return rc;
+            L2B_NCCL(ctx, g_nccl.AllReduce(ctx->delta, ctx->delta, dim, ncclFloat, ncclSum, ctx->comm, st));
+            resid_add_kernel<<<(dim + NT - 1) / NT, NT, 0, st>>>(ctx->X, ctx->delta, dim, ctx->ctl);
+            L2B_CUDA(ctx, cudaGetLastError());
+            ++ctx->last_launches;
+        }
+        return rc;
     };
     for (int l = 0; l < c.n_layers; ++l) {
         // ---- rmsnorm + q,k,v + RoPE + KV append (:305-358)
         GemvParams p{};
         p.ctl = ctx->ctl;
         p.n = dim;
-        const bool p2p = ctx->world > 1 && ctx->use_p2p;
-        auto consume_slot = [&](GemvParams &g, int slot) {      // pending residual = sum of all ranks' partials
-            g.xparts = ctx->xchg + (size_t)slot * ctx->world * dim;
-            g.xflags = ctx->xflags + (size_t)slot * ctx->world;
-            g.xworld = ctx->world;
-            g.xcount_per_step = (dim + 1) / 2;     // counters count row pairs landed
-        };
-        auto produce_slot = [&](GemvParams &g, int slot) {      // my partial rows go to every rank
-            g.xworld = ctx->world;
-            for (int r = 0; r < ctx->world; ++r) {
-                g.xout_peer[r] = ctx->peer_xchg[r] + ((size_t)slot * ctx->world + ctx->rank) * dim;
-                g.xflag_peer[r] = ctx->peer_flags[r] + (size_t)slot * ctx->world + ctx->rank;
-            }
-        };
+        p.x_in = ctx->X;
         if (l == 0) {
             p.emb = ctx->emb;                 // :295-296
+            p.x_out = ctx->X;
             p.bump_epoch = 1;
-        } else {
-            p.x_in = ctx->X[cur];
-            if (p2p) consume_slot(p, 2 * (l - 1) + 1);
-            else p.delta = ctx->delta_f;      // pending :422 of the previous layer
+        } else if (p2p) {
+            consume_slot(p, 2 * (l - 1) + 1); // pending :422 of the previous layer
         }
         p.gamma = ctx->rms_att + (size_t)l * dim;
-        p.x_out = ctx->X[cur ^ 1];
-        cur ^= 1;
         p.w0 = ctx->wq + (size_t)l * ctx->q_loc * dim;
         p.w1 = ctx->wk + (size_t)l * ctx->kv_loc * dim;
         p.w2 = ctx->wv + (size_t)l * ctx->kv_loc * dim;
@@ -522,7 +661,6 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
         p.vcache = ctx->vcache + loff;
         p.rope_cos = ctx->rope_cos; p.rope_sin = ctx->rope_sin;
         p.head_size = ctx->head_size; p.kv_dim = ctx->kv_loc;
-        set_pf(p, EPI_STORE, ctx->wo + (size_t)l * dim * ctx->q_loc, nullptr, nullptr, dim, 0, dim, ctx->q_loc);
         int rc = launch_gemv(ctx, EPI_QKV, p, st, "qkv_rope", l);
         if (rc) return rc;
 
@@ -530,138 +668,84 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax) {
         rc = launch_attention(ctx, l, st);
         if (rc) return rc;
 
-        // ---- wo (:392); the residual add (:395) is applied by the next kernel's prologue
+        // ---- wo + residual (:392-395)
         GemvParams o{};
         o.ctl = ctx->ctl;
         o.n = ctx->q_loc;
         o.x_in = ctx->xb;
         o.w0 = ctx->wo + (size_t)l * dim * ctx->q_loc;
-        o.total_rows = dim; o.rows0 = dim;
-        o.out0 = ctx->delta_a;
-        if (p2p) produce_slot(o, 2 * l);
-        set_pf(o, EPI_SILU, ctx->w1 + (size_t)l * ctx->hid_loc * dim, ctx->w3 + (size_t)l * ctx->hid_loc * dim, nullptr,
-               ctx->hid_loc, 0, 2 * ctx->hid_loc, dim);
-        rc = launch_gemv(ctx, p2p ? EPI_XCHG : EPI_STORE, o, st, "wo", l);
+        rc = residual_gemv(o, 2 * l, "wo", l);
         if (rc) return rc;
-        if (p2p) ctx->xgrid[2 * l] = ctx->last_grid;
-        else if (ctx->world > 1)
-            L2B_NCCL(ctx, g_nccl.AllReduce(ctx->delta_a, ctx->delta_a, dim, ncclFloat, ncclSum, ctx->comm, st));
 
-        // ---- residual + rmsnorm + w1,w3 + SiLU*mul (:395-416)
+        // ---- rmsnorm + w1,w3 + SiLU*mul (:398-416)
         GemvParams f{};
         f.ctl = ctx->ctl;
         f.n = dim;
-        f.x_in = ctx->X[cur];
+        f.x_in = ctx->X;
         if (p2p) consume_slot(f, 2 * l);
-        else f.delta = ctx->delta_a;
         f.gamma = ctx->rms_ffn + (size_t)l * dim;
-        f.x_out = ctx->X[cur ^ 1];
-        cur ^= 1;
         f.w0 = ctx->w1 + (size_t)l * ctx->hid_loc * dim;
         f.w1 = ctx->w3 + (size_t)l * ctx->hid_loc * dim;
         f.rows0 = ctx->hid_loc;
         f.total_rows = 2 * ctx->hid_loc;
         f.out0 = ctx->hb;
-        set_pf(f, EPI_STORE, ctx->w2 + (size_t)l * dim * ctx->hid_loc, nullptr, nullptr, dim, 0, dim, ctx->hid_loc);
         rc = launch_gemv(ctx, EPI_SILU, f, st, "w13_silu", l);
         if (rc) return rc;
 
-        // ---- w2 (:419); residual (:422) deferred likewise
+        // ---- w2 + residual (:419-422)
         GemvParams d{};
         d.ctl = ctx->ctl;
         d.n = ctx->hid_loc;
         d.x_in = ctx->hb;
         d.w0 = ctx->w2 + (size_t)l * dim * ctx->hid_loc;
-        d.total_rows = dim; d.rows0 = dim;
-        d.out0 = ctx->delta_f;
-        if (p2p) produce_slot(d, 2 * l + 1);
-        if (l + 1 < c.n_layers) pf_qkv(d, l + 1);
-        else set_pf(d, EPI_STORE, ctx->wcls, nullptr, nullptr, ctx->vocab_loc, 0, ctx->vocab_loc, dim);
-        rc = launch_gemv(ctx, p2p ? EPI_XCHG : EPI_STORE, d, st, "w2", l);
+        rc = residual_gemv(d, 2 * l + 1, "w2", l);
         if (rc) return rc;
-        if (p2p) ctx->xgrid[2 * l + 1] = ctx->last_grid;
-        else if (ctx->world > 1)
-            L2B_NCCL(ctx, g_nccl.AllReduce(ctx->delta_f, ctx->delta_f, dim, ncclFloat, ncclSum, ctx->comm, st));
     }
-    // ---- final residual + rmsnorm + classifier (:422-429)
+    // ---- final rmsnorm + classifier (:426-429)
     GemvParams k{};
     k.ctl = ctx->ctl;
     k.n = dim;
-    k.x_in = ctx->X[cur];
-    if (ctx->world > 1 && ctx->use_p2p) {
-        const int slot = 2 * (c.n_layers - 1) + 1;
-        k.xparts = ctx->xchg + (size_t)slot * ctx->world * dim;
-        k.xflags = ctx->xflags + (size_t)slot * ctx->world;
-        k.xworld = ctx->world;
-        k.xcount_per_step = (dim + 1) / 2;
-    } else {
-        k.delta = ctx->delta_f;
-    }
+    k.x_in = ctx->X;
+    if (p2p) consume_slot(k, 2 * (c.n_layers - 1) + 1);
     k.gamma = ctx->rms_final;
-    k.x_out = ctx->X[cur ^ 1];
-    cur ^= 1;
-    ctx->final_x = cur;
     k.w0 = ctx->wcls;
     k.total_rows = ctx->vocab_loc; k.rows0 = ctx->vocab_loc;
-    k.out0 = (ctx->world > 1) ? ctx->logits_loc : ctx->logits;
+    k.out0 = tp ? ctx->logits_loc : ctx->logits;
     k.amax = ctx->amax;
     k.row_base = ctx->rank * ctx->vocab_loc;
-    pf_qkv(k, 0);   // the next token starts with layer 0's q/k/v rows
-    int rc = launch_gemv(ctx, want_argmax ? EPI_ARGMAX : EPI_STORE, k, st, "classifier", -1);
-    if (rc) return rc;
-    if (ctx->world > 1) {
-        if (want_argmax)
-            L2B_NCCL(ctx, g_nccl.AllReduce(ctx->amax, ctx->amax, 1, ncclUint64, ncclMax, ctx->comm, st));
-        else
-            L2B_NCCL(ctx, g_nccl.AllGather(ctx->logits_loc, ctx->logits, ctx->vocab_loc, ncclFloat, ctx->comm, st));
+    const bool want_argmax = (mode == MODE_ARGMAX);
+    int epi = want_argmax ? EPI_ARGMAX : EPI_STORE;
+    const bool in_process = ctx->leader != nullptr;
+    if (p2p && !want_argmax) {
+        // logits slices travel as LL units: to every rank (one process per GPU: each rank's caller gets
+        // the logits), or to rank 0 only (in-process group: one caller)
+        epi = EPI_XCHG;
+        if (in_process) {
+            k.ll_ndst = 1;
+            k.ll_out[0] = ll_logits_at(ctx->peer_arena[0], ctx);
+        } else {
+            k.ll_ndst = ctx->world;
+            for (int r = 0; r < ctx->world; ++r) k.ll_out[r] = ll_logits_at(ctx->peer_arena[r], ctx);
+        }
     }
-    return L2B_OK;
-}
-
-int launch_mega(l2b_ctx *ctx, cudaStream_t st, bool want_argmax, bool do_advance) {
-    MegaParams mp{};
-    mp.emb = ctx->emb; mp.rms_att = ctx->rms_att; mp.rms_ffn = ctx->rms_ffn; mp.rms_final = ctx->rms_final;
-    mp.wq = ctx->wq; mp.wk = ctx->wk; mp.wv = ctx->wv; mp.wo = ctx->wo;
-    mp.w1 = ctx->w1; mp.w2 = ctx->w2; mp.w3 = ctx->w3; mp.wcls = ctx->wcls;
-    mp.X0 = ctx->X[0]; mp.X1 = ctx->X[1]; mp.delta_a = ctx->delta_a; mp.delta_f = ctx->delta_f;
-    mp.q = ctx->q; mp.xb = ctx->xb; mp.hb = ctx->hb;
-    mp.logits = (ctx->world > 1) ? ctx->logits_loc : ctx->logits;
-    mp.kcache = ctx->kcache; mp.vcache = ctx->vcache;
-    mp.rope_cos = ctx->rope_cos; mp.rope_sin = ctx->rope_sin;
-    mp.part_o = ctx->part_o; mp.part_ml = ctx->part_ml; mp.counters = ctx->counters;
-    mp.ctl = ctx->ctl; mp.amax = ctx->amax; mp.gbar = ctx->gbar;
-    mp.dim = ctx->dim; mp.hid_loc = ctx->hid_loc; mp.q_loc = ctx->q_loc; mp.kv_loc = ctx->kv_loc;
-    mp.heads_loc = ctx->heads_loc; mp.vocab_loc = ctx->vocab_loc; mp.n_layers = ctx->cfg.n_layers;
-    mp.seq_len = ctx->cfg.seq_len; mp.head_size = ctx->head_size; mp.kv_mul = ctx->kv_mul;
-    mp.nsplit = ctx->nsplit; mp.min_chunk = ctx->min_chunk;
-    mp.nstage = ctx->mega_nstage; mp.xs_floats = ctx->mega_xs_floats;
-    mp.want_argmax = want_argmax ? 1 : 0;
-    mp.row_base = ctx->rank * ctx->vocab_loc;
-    mp.do_advance = do_advance ? 1 : 0;
-    mp.world = ctx->world; mp.rank = ctx->rank;
-    for (int r = 0; r < ctx->world && r < MAX_TP; ++r) { mp.peer_xchg[r] = ctx->peer_xchg[r]; mp.peer_flags[r] = ctx->peer_flags[r]; }
-    mp.xchg = ctx->xchg; mp.xflags = ctx->xflags;
-    mp.forced = ctx->gen_forced; mp.out_next = ctx->gen_out; mp.n_done = ctx->gen_ndone;
-    void *args[] = {&mp};
-    L2B_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)mega_step_kernel, dim3(ctx->num_sms), dim3(MEGA_THREADS),
-                                              args, (size_t)ctx->mega_smem, st));
-    ++ctx->last_launches;
-    return L2B_OK;
-}
-
-// one decode step through the megakernel (+ the collectives a sharded context still needs)
-int enqueue_mega_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax, bool advance_after) {
-    const bool tp = ctx->world > 1;
-    int rc = launch_mega(ctx, st, want_argmax, advance_after && !tp);
+    int rc = launch_gemv(ctx, epi, k, st, "classifier", -1);
     if (rc) return rc;
     if (tp) {
-        if (want_argmax) {
-            L2B_NCCL(ctx, g_nccl.AllReduce(ctx->amax, ctx->amax, 1, ncclUint64, ncclMax, ctx->comm, st));
-            if (advance_after) {
-                advance_kernel<<<1, 1, 0, st>>>(ctx->ctl, ctx->amax, ctx->gen_forced, ctx->gen_out, ctx->gen_ndone);
-                L2B_CUDA(ctx, cudaGetLastError());
-                ++ctx->last_launches;
+        if (p2p) {
+            if (!want_argmax && (!in_process || ctx->rank == 0)) {
+                float *lg = ctx->logits;
+                const unsigned long long *in = ll_logits_at(ctx->arena, ctx);
+                int V = c.vocab_size;
+                const int *ctl = ctx->ctl;
+                unsigned long long spin = ctx->spin_ns;
+                void *args[] = {&lg, &in, &V, &ctl, &spin};
+                int blocks = (V / 2 + NT - 1) / NT;
+                if (blocks > ctx->num_sms) blocks = ctx->num_sms;
+                rc = launch_small(ctx, (const void *)gather_logits_kernel, dim3(blocks), dim3(NT), args, st, true);
+                if (rc) return rc;
             }
+        } else if (want_argmax) {
+            L2B_NCCL(ctx, g_nccl.AllReduce(ctx->amax, ctx->amax, 1, ncclUint64, ncclMax, ctx->comm, st));
         } else {
             L2B_NCCL(ctx, g_nccl.AllGather(ctx->logits_loc, ctx->logits, ctx->vocab_loc, ncclFloat, ctx->comm, st));
         }
@@ -669,30 +753,66 @@ int enqueue_mega_step(l2b_ctx *ctx, cudaStream_t st, bool want_argmax, bool adva
     return L2B_OK;
 }
 
+int launch_sample_prep(l2b_ctx *ctx, cudaStream_t st) {
+    float *lg = ctx->logits;
+    int V = ctx->cfg.vocab_size;
+    const int *ctl = ctx->ctl;
+    ProbIndex *cand = ctx->cand;
+    int cap = kCandCap;
+    int *n_cand = ctx->n_cand;
+    void *args[] = {&lg, &V, &ctl, &cand, &cap, &n_cand};
+    return launch_small(ctx, (const void *)sample_prep_kernel, dim3(1), dim3(SAMP_THREADS), args, st, true);
+}
+
+// everything one call needs, as it is captured into (or eagerly enqueued instead of) graph `which`
+int enqueue_call(l2b_ctx *ctx, cudaStream_t st, int which) {
+    const bool sink = !ctx->leader || ctx->rank == 0;   // in-process group: only rank 0 returns data to the host
+    if (which != G_ARGMAX_LOOP)
+        L2B_CUDA(ctx, cudaMemcpyAsync(ctx->ctl, ctx->h_ctl, CTL_HOST_WORDS * sizeof(int), cudaMemcpyHostToDevice, st));
+    const StepMode mode = (which == G_LOGITS) ? MODE_LOGITS : (which == G_SAMPLE) ? MODE_SAMPLE : MODE_ARGMAX;
+    int rc = enqueue_step(ctx, st, mode);
+    if (rc) return rc;
+    const size_t vbytes = (size_t)ctx->cfg.vocab_size * sizeof(float);
+    switch (which) {
+    case G_LOGITS:
+        if (sink) L2B_CUDA(ctx, cudaMemcpyAsync(ctx->h_logits, ctx->logits, vbytes, cudaMemcpyDeviceToHost, st));
+        break;
+    case G_SAMPLE:
+        if (sink) {
+            rc = launch_sample_prep(ctx, st);
+            if (rc) return rc;
+            L2B_CUDA(ctx, cudaMemcpyAsync(ctx->h_logits, ctx->logits, vbytes, cudaMemcpyDeviceToHost, st));
+            L2B_CUDA(ctx, cudaMemcpyAsync(ctx->h_cand, ctx->cand, (size_t)kCandCap * sizeof(ProbIndex), cudaMemcpyDeviceToHost, st));
+            L2B_CUDA(ctx, cudaMemcpyAsync(ctx->h_ints + 2, ctx->n_cand, sizeof(int), cudaMemcpyDeviceToHost, st));
+        }
+        break;
+    case G_ARGMAX_ONE:
+        rc = launch_advance(ctx, st, false, ctx->world > 1 && ctx->use_p2p);
+        if (rc) return rc;
+        if (sink) L2B_CUDA(ctx, cudaMemcpyAsync(ctx->h_ints, ctx->gen_out, sizeof(int), cudaMemcpyDeviceToHost, st));
+        break;
+    default:   // G_ARGMAX_LOOP
+        rc = launch_advance(ctx, st, true, ctx->world > 1 && ctx->use_p2p);
+        if (rc) return rc;
+        break;
+    }
+    if (which != G_ARGMAX_LOOP)
+        L2B_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctl + CTL_WORDS, ctx->ctl, CTL_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
+    return L2B_OK;
+}
+
 int build_graphs(l2b_ctx *ctx) {
-    for (int which = 0; which < 2; ++which) {
+    for (int which = 0; which < G_COUNT; ++which) {
         cudaGraph_t g = nullptr;
         L2B_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
         ctx->last_launches = 0;
-        int rc = enqueue_step(ctx, ctx->stream, which == 1);
-        if (rc == L2B_OK) {
-            if (which == 0) {
-                cudaError_t e = cudaMemcpyAsync(ctx->h_logits, ctx->logits, (size_t)ctx->cfg.vocab_size * 4,
-                                                cudaMemcpyDeviceToHost, ctx->stream);
-                if (e != cudaSuccess) rc = fail(ctx, L2B_ERR_CUDA, cudaGetErrorString(e));
-            } else {
-                advance_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, ctx->amax, ctx->gen_forced, ctx->gen_out,
-                                                         ctx->gen_ndone);
-                ++ctx->last_launches;
-            }
-        }
+        int rc = enqueue_call(ctx, ctx->stream, which);
         cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
         if (rc) { if (g) cudaGraphDestroy(g); return rc; }
         L2B_CUDA(ctx, e);
-        cudaGraphExec_t *dst = which == 0 ? &ctx->graph_logits : &ctx->graph_argmax;
-        L2B_CUDA(ctx, cudaGraphInstantiate(dst, g, 0));
+        L2B_CUDA(ctx, cudaGraphInstantiate(&ctx->graphs[which], g, 0));
         L2B_CUDA(ctx, cudaGraphDestroy(g));
-        if (which == 0) ctx->launches_per_step = ctx->last_launches;
+        if (which == G_LOGITS) ctx->launches_per_step = ctx->last_launches;
     }
     return L2B_OK;
 }
@@ -705,33 +825,27 @@ int check_step_args(l2b_ctx *ctx, int token, int pos) {
     return L2B_OK;
 }
 
-int common_create(l2b_ctx **out, const l2b_config *cfg, const Source &src, uint64_t n_floats,
-                  const float *rope_cos, const float *rope_sin, const l2b_shard *shard) {
-    if (!out || !cfg) { g_create_error = "NULL argument"; return L2B_ERR_INVALID_ARG; }
-    *out = nullptr;
-    const int world = shard ? shard->world_size : 1;
-    const int rank = shard ? shard->rank : 0;
-    std::string why;
-    int rc = validate_config(cfg, world, &why);
-    if (rc) { g_create_error = why; return rc; }
-    if (rank < 0 || rank >= world) { g_create_error = "rank out of range"; return L2B_ERR_INVALID_ARG; }
-    if (src.host && n_floats < checkpoint_floats(cfg)) {
-        g_create_error = "host_weights shorter than the checkpoint layout requires";
-        return L2B_ERR_INVALID_ARG;
-    }
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        g_create_error = "no CUDA device";
-        return L2B_ERR_NO_DEVICE;
-    }
-    const int device = shard ? shard->device : 0;
-    if (device < 0 || device >= ndev) { g_create_error = "device ordinal out of range"; return L2B_ERR_INVALID_ARG; }
-    cudaDeviceProp prop{};
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { g_create_error = "cudaGetDeviceProperties failed"; return L2B_ERR_CUDA; }
-    if (prop.major != 10) { g_create_error = "device is not compute capability 10.x (built for sm_100a only)"; return L2B_ERR_NO_DEVICE; }
+#define L2B_TRY(expr)                                  \
+    do {                                               \
+        int rc__ = (expr);                             \
+        if (rc__) {                                    \
+            g_create_error = ctx->err;                 \
+            return rc__;                               \
+        }                                              \
+    } while (0)
 
-    l2b_ctx *ctx = new l2b_ctx();
+int cuda_try(l2b_ctx *ctx, cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return L2B_OK;
+    ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? L2B_ERR_OOM : L2B_ERR_CUDA;
+}
+
+// ---- creation, stage 1: weights + run state of one rank (no peer is touched) ------------------
+int create_rank(l2b_ctx *ctx, const l2b_config *cfg, const Source &src, const float *rope_cos,
+                const float *rope_sin, int rank, int world, int device) {
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { ctx->err = "cudaGetDeviceProperties failed"; g_create_error = ctx->err; return L2B_ERR_CUDA; }
+    if (prop.major != 10) { ctx->err = "device is not compute capability 10.x (built for sm_100a only)"; g_create_error = ctx->err; return L2B_ERR_NO_DEVICE; }
     ctx->cfg = *cfg;
     ctx->rank = rank; ctx->world = world; ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
@@ -745,25 +859,10 @@ int common_create(l2b_ctx **out, const l2b_config *cfg, const Source &src, uint6
     ctx->heads_loc = cfg->n_heads / world;
     ctx->vocab_loc = cfg->vocab_size / world;
 
-#define L2B_TRY(expr)                                  \
-    do {                                               \
-        int rc__ = (expr);                             \
-        if (rc__) {                                    \
-            g_create_error = ctx->err;                 \
-            l2b_destroy(ctx);                          \
-            return rc__;                               \
-        }                                              \
-    } while (0)
-    auto cuda_try = [&](cudaError_t e, const char *what) -> int {
-        if (e == cudaSuccess) return L2B_OK;
-        ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
-        return e == cudaErrorMemoryAllocation ? L2B_ERR_OOM : L2B_ERR_CUDA;
-    };
-
-    L2B_TRY(cuda_try(cudaSetDevice(device), "cudaSetDevice"));
-    L2B_TRY(cuda_try(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate"));
-    L2B_TRY(cuda_try(cudaEventCreate(&ctx->ev0), "cudaEventCreate"));
-    L2B_TRY(cuda_try(cudaEventCreate(&ctx->ev1), "cudaEventCreate"));
+    L2B_TRY(cuda_try(ctx, cudaSetDevice(device), "cudaSetDevice"));
+    L2B_TRY(cuda_try(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate"));
+    L2B_TRY(cuda_try(ctx, cudaEventCreate(&ctx->ev0), "cudaEventCreate"));
+    L2B_TRY(cuda_try(ctx, cudaEventCreate(&ctx->ev1), "cudaEventCreate"));
 
     const uint64_t dim = cfg->dim, hid = cfg->hidden_dim, L = cfg->n_layers, V = cfg->vocab_size, S = cfg->seq_len;
     const uint64_t hs = ctx->head_size, kvd = ctx->kv_dim;
@@ -785,6 +884,7 @@ int common_create(l2b_ctx **out, const l2b_config *cfg, const Source &src, uint6
     off += 2 * (S * hs / 2);     // freq_cis_real/imag: not used by transformer() (:67-69, :298-300)
     const uint64_t o_wcls = off;
 
+    const auto t_load0 = std::chrono::steady_clock::now();
     L2B_TRY(materialize(ctx, &ctx->emb, src, o_emb, 1, 1, V, dim, SH_NONE, {0.0, 0.04, -BIG, BIG}));
     L2B_TRY(materialize(ctx, &ctx->rms_att, src, o_ratt, 2, 1, L, dim, SH_NONE, {1.35, 0.35, 0.25f, 2.4f}));
     L2B_TRY(materialize(ctx, &ctx->wq, src, o_wq, 3, L, dim, dim, SH_ROWS, {0.0, 0.04 * sd, -BIG, BIG}));
@@ -800,14 +900,17 @@ int common_create(l2b_ctx **out, const l2b_config *cfg, const Source &src, uint6
         ctx->wcls = ctx->emb + (size_t)rank * ctx->vocab_loc * dim;   // :112
     } else {
         L2B_TRY(materialize(ctx, &ctx->wcls, src, o_wcls, 14, 1, V, dim, SH_ROWS, {0.0, 0.04, -BIG, BIG}));
-        ctx->wcls_owned = true;
+    }
+    L2B_TRY(cuda_try(ctx, cudaStreamSynchronize(ctx->stream), "weight upload"));
+    ctx->load_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_load0).count();
+    for (int i = 0; i < 2; ++i) {          // the staging buffers are only needed during the upload
+        if (ctx->stage[i]) { cudaFreeHost(ctx->stage[i]); ctx->stage[i] = nullptr; }
+        if (ctx->stage_ev[i]) { cudaEventDestroy(ctx->stage_ev[i]); ctx->stage_ev[i] = nullptr; }
     }
 
     // ---- run state
-    L2B_TRY(dev_alloc(ctx, &ctx->X[0], dim));
-    L2B_TRY(dev_alloc(ctx, &ctx->X[1], dim));
-    L2B_TRY(dev_alloc(ctx, &ctx->delta_a, dim));
-    L2B_TRY(dev_alloc(ctx, &ctx->delta_f, dim));
+    L2B_TRY(dev_alloc(ctx, &ctx->X, dim));
+    L2B_TRY(dev_alloc(ctx, &ctx->delta, dim));
     L2B_TRY(dev_alloc(ctx, &ctx->q, (size_t)ctx->q_loc));
     L2B_TRY(dev_alloc(ctx, &ctx->xb, (size_t)ctx->q_loc));
     L2B_TRY(dev_alloc(ctx, &ctx->hb, (size_t)ctx->hid_loc));
@@ -822,11 +925,14 @@ int common_create(l2b_ctx **out, const l2b_config *cfg, const Source &src, uint6
     L2B_TRY(dev_alloc(ctx, &ctx->gen_forced, S));
     L2B_TRY(dev_alloc(ctx, &ctx->gen_out, S));
     L2B_TRY(dev_alloc(ctx, &ctx->gen_ndone, (size_t)1));
-    L2B_TRY(cuda_try(cudaMemsetAsync(ctx->ctl, 0, CTL_WORDS * sizeof(int), ctx->stream), "memset"));
-    L2B_TRY(cuda_try(cudaMemsetAsync(ctx->amax, 0, sizeof(unsigned long long), ctx->stream), "memset"));
-    L2B_TRY(cuda_try(cudaMemsetAsync(ctx->gen_forced, 0xff, S * sizeof(int), ctx->stream), "memset"));
-    L2B_TRY(cuda_try(cudaMemsetAsync(ctx->kcache, 0, L * S * ctx->kv_loc * sizeof(float), ctx->stream), "memset"));
-    L2B_TRY(cuda_try(cudaMemsetAsync(ctx->vcache, 0, L * S * ctx->kv_loc * sizeof(float), ctx->stream), "memset"));
+    L2B_TRY(dev_alloc(ctx, &ctx->cand, (size_t)kCandCap));
+    L2B_TRY(dev_alloc(ctx, &ctx->n_cand, (size_t)1));
+    L2B_TRY(cuda_try(ctx, cudaMemsetAsync(ctx->ctl, 0, CTL_WORDS * sizeof(int), ctx->stream), "memset"));
+    L2B_TRY(cuda_try(ctx, cudaMemsetAsync(ctx->X, 0, dim * sizeof(float), ctx->stream), "memset"));
+    L2B_TRY(cuda_try(ctx, cudaMemsetAsync(ctx->amax, 0, sizeof(unsigned long long), ctx->stream), "memset"));
+    L2B_TRY(cuda_try(ctx, cudaMemsetAsync(ctx->gen_forced, 0xff, S * sizeof(int), ctx->stream), "memset"));
+    L2B_TRY(cuda_try(ctx, cudaMemsetAsync(ctx->kcache, 0, L * S * ctx->kv_loc * sizeof(float), ctx->stream), "memset"));
+    L2B_TRY(cuda_try(ctx, cudaMemsetAsync(ctx->vcache, 0, L * S * ctx->kv_loc * sizeof(float), ctx->stream), "memset"));
 
     // ---- attention launch shape: enough (head, split) CTAs to cover the SMs, chunks >= min_chunk positions
     {
@@ -845,46 +951,13 @@ int common_create(l2b_ctx **out, const l2b_config *cfg, const Source &src, uint6
         if (ctx->attn_smem > kMaxDynSmem) {
             ctx->err = "seq_len too large for the attention kernel's shared memory";
             g_create_error = ctx->err;
-            l2b_destroy(ctx);
             return L2B_ERR_UNSUPPORTED;
         }
-        L2B_TRY(cuda_try(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), "cudaFuncSetAttribute"));
+        L2B_TRY(cuda_try(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), "cudaFuncSetAttribute"));
         L2B_TRY(dev_alloc(ctx, &ctx->part_o, (size_t)ctx->heads_loc * ns * hs));
         L2B_TRY(dev_alloc(ctx, &ctx->part_ml, (size_t)ctx->heads_loc * ns * 2));
         L2B_TRY(dev_alloc(ctx, &ctx->counters, (size_t)ctx->heads_loc));
-        L2B_TRY(cuda_try(cudaMemsetAsync(ctx->counters, 0, ctx->heads_loc * sizeof(unsigned int), ctx->stream), "memset"));
-    }
-
-    // ---- persistent megakernel: shared-memory budget = ring + activation/attention scratch
-    {
-        L2B_TRY(dev_alloc(ctx, &ctx->gbar, (size_t)64));
-        L2B_TRY(cuda_try(cudaMemsetAsync(ctx->gbar, 0, 64 * sizeof(unsigned long long), ctx->stream), "memset"));
-        size_t xs = (size_t)ctx->dim;
-        if ((size_t)ctx->hid_loc > xs) xs = ctx->hid_loc;
-        if ((size_t)ctx->q_loc > xs) xs = ctx->q_loc;
-        const size_t attn_need = (size_t)ctx->attn_smem / sizeof(float);
-        if (attn_need > xs) xs = attn_need;
-        xs = (xs + 3) & ~(size_t)3;
-        const size_t stage_bytes = (size_t)TMA_STAGE_FLOATS * 4;
-        int ns = (int)(((size_t)kMaxSmemOptin - xs * 4) / stage_bytes);
-        if (ns > TMA_MAX_STAGES) ns = TMA_MAX_STAGES;
-        ctx->mega_nstage = ns;
-        ctx->mega_xs_floats = (int)xs;
-        ctx->mega_smem = (int)(ns * stage_bytes + xs * 4);
-        int coop = 0;
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-        // opt-in: measured slower than the CUDA-graph + PDL chain on every workload so far
-        // (profiles/r01_megakernel.md) — the per-phase grid barrier + activation staging chain
-        // (~6 us) costs more than a PDL kernel boundary (~3.4 us)
-        const char *envm = getenv("L2B_MEGA");
-        const bool want = envm && envm[0] == '1';
-        ctx->use_mega = want && coop && ns >= 2 && hs <= 256;
-        if (ctx->use_mega) {
-            L2B_TRY(cuda_try(cudaFuncSetAttribute(mega_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin), "cudaFuncSetAttribute(mega)"));
-            int occ = 0;
-            L2B_TRY(cuda_try(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mega_step_kernel, MEGA_THREADS, ctx->mega_smem), "occupancy(mega)"));
-            if (occ < 1) ctx->use_mega = false;
-        }
+        L2B_TRY(cuda_try(ctx, cudaMemsetAsync(ctx->counters, 0, ctx->heads_loc * sizeof(unsigned int), ctx->stream), "memset"));
     }
 
     // ---- RoPE table (:338-342); the host's own libm values when the caller passes them
@@ -903,94 +976,33 @@ int common_create(l2b_ctx **out, const l2b_config *cfg, const Source &src, uint6
                     hsn[p * (hs / 2) + j] = sinf(val);                                       // :342
                 }
         }
-        L2B_TRY(cuda_try(cudaMemcpy(ctx->rope_cos, hc.data(), hc.size() * sizeof(float), cudaMemcpyHostToDevice), "rope upload"));
-        L2B_TRY(cuda_try(cudaMemcpy(ctx->rope_sin, hsn.data(), hsn.size() * sizeof(float), cudaMemcpyHostToDevice), "rope upload"));
+        L2B_TRY(cuda_try(ctx, cudaMemcpy(ctx->rope_cos, hc.data(), hc.size() * sizeof(float), cudaMemcpyHostToDevice), "rope upload"));
+        L2B_TRY(cuda_try(ctx, cudaMemcpy(ctx->rope_sin, hsn.data(), hsn.size() * sizeof(float), cudaMemcpyHostToDevice), "rope upload"));
     }
 
     // ---- pinned host buffers
-    L2B_TRY(cuda_try(cudaHostAlloc((void **)&ctx->h_logits, V * sizeof(float), cudaHostAllocDefault), "cudaHostAlloc"));
-    L2B_TRY(cuda_try(cudaHostAlloc((void **)&ctx->h_ints, 16 * sizeof(int), cudaHostAllocDefault), "cudaHostAlloc"));
-    L2B_TRY(cuda_try(cudaHostAlloc((void **)&ctx->h_gen, S * sizeof(int), cudaHostAllocDefault), "cudaHostAlloc"));
+    L2B_TRY(cuda_try(ctx, cudaHostAlloc((void **)&ctx->h_logits, V * sizeof(float), cudaHostAllocDefault), "cudaHostAlloc"));
+    L2B_TRY(cuda_try(ctx, cudaHostAlloc((void **)&ctx->h_ctl, 2 * CTL_WORDS * sizeof(int), cudaHostAllocDefault), "cudaHostAlloc"));
+    L2B_TRY(cuda_try(ctx, cudaHostAlloc((void **)&ctx->h_ints, 16 * sizeof(int), cudaHostAllocDefault), "cudaHostAlloc"));
+    L2B_TRY(cuda_try(ctx, cudaHostAlloc((void **)&ctx->h_gen, S * sizeof(int), cudaHostAllocDefault), "cudaHostAlloc"));
+    L2B_TRY(cuda_try(ctx, cudaHostAlloc((void **)&ctx->h_cand, (size_t)kCandCap * sizeof(ProbIndex), cudaHostAllocDefault), "cudaHostAlloc"));
+    memset(ctx->h_ctl, 0, 2 * CTL_WORDS * sizeof(int));
 
-    // ---- communicator
+    // ---- tensor-parallel landing areas: one zeroed arena
     if (world > 1) {
-        std::string e;
-        if (!nccl_load(&e)) { ctx->err = e; g_create_error = e; l2b_destroy(ctx); return L2B_ERR_COMM; }
-        ncclUniqueId id;
-        memcpy(&id, shard->comm_id, sizeof id);
-        ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
-        if (r != ncclSuccess) {
-            ctx->err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r);
-            g_create_error = ctx->err;
-            l2b_destroy(ctx);
-            return L2B_ERR_COMM;
-        }
-    }
-
-    // ---- fused all-reduce over peer memory: exchange buffers shared through CUDA IPC
-    if (world > 1) {
-        const char *mode = getenv("L2B_TP");
-        const bool want = !(mode && strcmp(mode, "nccl") == 0);
         const size_t slots = 2 * (size_t)L;
-        ctx->xgrid.assign(slots, 0);
-        int ok = want ? 1 : 0;
-        cudaIpcMemHandle_t hx{}, hf{};
-        if (ok) {
-            L2B_TRY(dev_alloc(ctx, &ctx->xchg, slots * world * dim));
-            L2B_TRY(dev_alloc(ctx, &ctx->xflags, slots * world));
-            L2B_TRY(cuda_try(cudaMemsetAsync(ctx->xflags, 0, slots * world * sizeof(unsigned int), ctx->stream), "memset"));
-            L2B_TRY(cuda_try(cudaMemsetAsync(ctx->xchg, 0, slots * world * dim * sizeof(float), ctx->stream), "memset"));
-            if (cudaIpcGetMemHandle(&hx, ctx->xchg) != cudaSuccess || cudaIpcGetMemHandle(&hf, ctx->xflags) != cudaSuccess) {
-                cudaGetLastError();
-                ok = 0;
-            }
-        }
-        // every rank learns every rank's handles (and whether it could make them) through NCCL
-        struct Msg { cudaIpcMemHandle_t hx, hf; int ok; int pad[3]; };
-        static_assert(sizeof(Msg) % 16 == 0, "Msg must be 16-byte sized");
-        Msg mine{hx, hf, ok, {0, 0, 0}};
-        Msg *d_all = nullptr;
-        L2B_TRY(dev_alloc(ctx, &d_all, (size_t)world));
-        L2B_TRY(cuda_try(cudaMemcpyAsync(d_all + rank, &mine, sizeof(Msg), cudaMemcpyHostToDevice, ctx->stream), "msg upload"));
-        {
-            ncclResult_t r = g_nccl.AllGather(d_all + rank, d_all, sizeof(Msg), ncclChar, ctx->comm, ctx->stream);
-            if (r != ncclSuccess) { ctx->err = "ncclAllGather(ipc handles) failed"; g_create_error = ctx->err; l2b_destroy(ctx); return L2B_ERR_COMM; }
-        }
-        std::vector<Msg> all(world);
-        L2B_TRY(cuda_try(cudaMemcpyAsync(all.data(), d_all, sizeof(Msg) * world, cudaMemcpyDeviceToHost, ctx->stream), "msg download"));
-        L2B_TRY(cuda_try(cudaStreamSynchronize(ctx->stream), "ipc exchange"));
-        for (int r = 0; r < world; ++r) ok = ok && all[r].ok;
-        if (ok) {
-            for (int r = 0; r < world && ok; ++r) {
-                if (r == rank) { ctx->peer_xchg[r] = ctx->xchg; ctx->peer_flags[r] = ctx->xflags; continue; }
-                void *px = nullptr, *pf = nullptr;
-                if (cudaIpcOpenMemHandle(&px, all[r].hx, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-                    cudaIpcOpenMemHandle(&pf, all[r].hf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-                    cudaGetLastError();
-                    ok = 0;
-                    break;
-                }
-                ctx->ipc_opened.push_back(px);
-                ctx->ipc_opened.push_back(pf);
-                ctx->peer_xchg[r] = (float *)px;
-                ctx->peer_flags[r] = (unsigned int *)pf;
-            }
-        }
-        // all ranks must take the same path: agree through a max-reduce of the failure bit
-        int *d_bad = nullptr;
-        L2B_TRY(dev_alloc(ctx, &d_bad, (size_t)1));
-        int bad = ok ? 0 : 1;
-        L2B_TRY(cuda_try(cudaMemcpyAsync(d_bad, &bad, sizeof(int), cudaMemcpyHostToDevice, ctx->stream), "flag upload"));
-        {
-            ncclResult_t r = g_nccl.AllReduce(d_bad, d_bad, 1, ncclInt, ncclMax, ctx->comm, ctx->stream);
-            if (r != ncclSuccess) { ctx->err = "ncclAllReduce(ipc agreement) failed"; g_create_error = ctx->err; l2b_destroy(ctx); return L2B_ERR_COMM; }
-        }
-        L2B_TRY(cuda_try(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "flag download"));
-        L2B_TRY(cuda_try(cudaStreamSynchronize(ctx->stream), "ipc agreement"));
-        ctx->use_p2p = (bad == 0);
+        size_t o = 0;
+        ctx->off_red = o;    o += slots * world * dim * sizeof(unsigned long long);
+        ctx->off_logits = o; o += (size_t)V * sizeof(unsigned long long);
+        ctx->off_amax = o;   o += (size_t)world * 2 * sizeof(unsigned long long);
+        o = (o + 255) & ~(size_t)255;
+        ctx->off_rdone = o;  o += slots * sizeof(unsigned int);
+        ctx->arena_bytes = (o + 255) & ~(size_t)255;
+        L2B_TRY(dev_alloc(ctx, &ctx->arena, ctx->arena_bytes));
+        L2B_TRY(cuda_try(ctx, cudaMemsetAsync(ctx->arena, 0, ctx->arena_bytes, ctx->stream), "memset"));
+        ctx->peer_arena[rank] = ctx->arena;
     }
 
-    L2B_TRY(cuda_try(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize"));
     {
         const char *env = getenv("L2B_NO_GRAPH");
         ctx->use_graphs = !(env && env[0] == '1');
@@ -1004,78 +1016,266 @@ int common_create(l2b_ctx **out, const l2b_config *cfg, const Source &src, uint6
         if (env5) ctx->tma_stages = atoi(env5);
         const char *enva = getenv("L2B_ATTN");
         if (enva && strcmp(enva, "3pass") == 0) ctx->attn_flash = false;
+        const char *envs = getenv("L2B_SPIN_TIMEOUT_MS");
+        if (envs && atoll(envs) > 0) ctx->spin_ns = (unsigned long long)atoll(envs) * 1000000ull;
         const char *envt = getenv("L2B_TRACE");
         if (envt && envt[0] == '1') {
-            ctx->trace_launches = 5 * cfg->n_layers + 2;
+            ctx->trace_launches = 5 * cfg->n_layers + 4;
             L2B_TRY(dev_alloc(ctx, &ctx->trace, (size_t)ctx->trace_launches * TRACE_MAX_CTAS * TRACE_SLOTS));
-            L2B_TRY(cuda_try(cudaMemset(ctx->trace, 0, (size_t)ctx->trace_launches * TRACE_MAX_CTAS * TRACE_SLOTS * 8), "memset"));
+            L2B_TRY(cuda_try(ctx, cudaMemset(ctx->trace, 0, (size_t)ctx->trace_launches * TRACE_MAX_CTAS * TRACE_SLOTS * 8), "memset"));
         }
-        const char *env7 = getenv("L2B_PF_KB");
-        if (env7) ctx->pf_bytes = atoi(env7) * 1024;
         const char *env6 = getenv("L2B_TMA_CTAS");
         if (env6) ctx->tma_ctas_per_sm = atoi(env6) > 0 ? atoi(env6) : 1;
     }
-    // one eager step of each flavour: sets function attributes outside capture and surfaces
-    // launch errors before a graph hides them (it scribbles on KV row 0, rewritten by step 0)
-    {
-        set_ctl_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, 0, 0, 0, ctx->amax);
-        L2B_TRY(enqueue_step(ctx, ctx->stream, false));
-        L2B_TRY(enqueue_step(ctx, ctx->stream, true));
-        advance_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, ctx->amax, ctx->gen_forced, ctx->gen_out, ctx->gen_ndone);
-        L2B_TRY(cuda_try(cudaStreamSynchronize(ctx->stream), "warm-up step"));
-        L2B_TRY(cuda_try(cudaGetLastError(), "warm-up step"));
-        if (ctx->use_mega) {
-            set_ctl_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, 0, 0, 0, ctx->amax);
-            L2B_TRY(enqueue_mega_step(ctx, ctx->stream, false, false));
-            L2B_TRY(enqueue_mega_step(ctx, ctx->stream, true, true));
-            L2B_TRY(cuda_try(cudaStreamSynchronize(ctx->stream), "warm-up megakernel step"));
-            L2B_TRY(cuda_try(cudaGetLastError(), "warm-up megakernel step"));
-        }
-    }
-    if (ctx->use_graphs) L2B_TRY(build_graphs(ctx));
-#undef L2B_TRY
-    *out = ctx;
+    L2B_TRY(cuda_try(ctx, cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize"));
     return L2B_OK;
 }
 
-// run one step; which: 0 = logits to pinned host, 1 = argmax
-int run_step(l2b_ctx *ctx, int token, int pos, int which) {
-    L2B_CUDA(ctx, cudaSetDevice(ctx->device));
-    ctx->last_launches = 0;
-    L2B_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (which == 1)   // a previous generate() may have left a forced token in slot 0
-        L2B_CUDA(ctx, cudaMemsetAsync(ctx->gen_forced, 0xff, sizeof(int), ctx->stream));
-    set_ctl_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, token, pos, 0, ctx->amax);
-    L2B_CUDA(ctx, cudaGetLastError());
-    if (ctx->use_mega) {
-        int rc = enqueue_mega_step(ctx, ctx->stream, which == 1, which == 1);
-        if (rc) return rc;
-        if (which == 0)
-            L2B_CUDA(ctx, cudaMemcpyAsync(ctx->h_logits, ctx->logits, (size_t)ctx->cfg.vocab_size * 4,
-                                          cudaMemcpyDeviceToHost, ctx->stream));
-    } else if (ctx->use_graphs) {
-        L2B_CUDA(ctx, cudaGraphLaunch(which == 0 ? ctx->graph_logits : ctx->graph_argmax, ctx->stream));
-        ctx->last_launches = ctx->launches_per_step + (which ? 1 : 0);
-    } else {
-        int rc = enqueue_step(ctx, ctx->stream, which == 1);
-        if (rc) return rc;
-        if (which == 0) {
-            L2B_CUDA(ctx, cudaMemcpyAsync(ctx->h_logits, ctx->logits, (size_t)ctx->cfg.vocab_size * 4,
-                                          cudaMemcpyDeviceToHost, ctx->stream));
-        } else {
-            advance_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, ctx->amax, ctx->gen_forced, ctx->gen_out,
-                                                     ctx->gen_ndone);
-            L2B_CUDA(ctx, cudaGetLastError());
-            ++ctx->last_launches;
+// ---- creation, stage 2: one eager call of each flavour on every local rank.  It sets function
+// attributes outside capture and surfaces launch errors before a graph hides them (it scribbles
+// on KV row 0, rewritten by step 0).  Tensor-parallel ranks exchange data during these steps, so
+// all local ranks are enqueued before any is synchronised.
+int warm_up(const std::vector<l2b_ctx *> &ranks) {
+    for (int which = 0; which < G_COUNT; ++which) {
+        for (l2b_ctx *ctx : ranks) {
+            L2B_TRY(cuda_try(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+            memset(ctx->h_ctl, 0, CTL_WORDS * sizeof(int));
+            ctx->h_ctl[CTL_TEMP] = 0x3f800000;   // 1.0f
+            ctx->h_ctl[CTL_TOPP] = 0x3f666666;   // 0.9f
+            if (which == G_ARGMAX_LOOP)
+                L2B_TRY(cuda_try(ctx, cudaMemcpyAsync(ctx->ctl, ctx->h_ctl, CTL_HOST_WORDS * sizeof(int), cudaMemcpyHostToDevice, ctx->stream), "ctl upload"));
+            L2B_TRY(enqueue_call(ctx, ctx->stream, which));
+        }
+        for (l2b_ctx *ctx : ranks) {
+            L2B_TRY(cuda_try(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+            L2B_TRY(cuda_try(ctx, cudaStreamSynchronize(ctx->stream), "warm-up step"));
+            L2B_TRY(cuda_try(ctx, cudaGetLastError(), "warm-up step"));
+            if (ctx->h_ctl[CTL_WORDS + CTL_ERR] && which != G_ARGMAX_LOOP) {
+                ctx->err = "tensor-parallel warm-up step timed out waiting for a peer";
+                g_create_error = ctx->err;
+                return L2B_ERR_COMM;
+            }
         }
     }
-    ++ctx->last_launches;  // set_ctl
-    if (which == 1)
-        L2B_CUDA(ctx, cudaMemcpyAsync(ctx->h_ints, ctx->gen_out, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    L2B_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    L2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    L2B_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
-    if (pos + 1 > ctx->n_appended) ctx->n_appended = pos + 1;
+    for (l2b_ctx *ctx : ranks) {
+        L2B_TRY(cuda_try(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
+        if (ctx->use_graphs) L2B_TRY(build_graphs(ctx));
+    }
+    return L2B_OK;
+}
+
+// ---- one process per GPU: communicator + CUDA IPC exchange of the arena handles ---------------
+int connect_ipc(l2b_ctx *ctx, const l2b_shard *shard) {
+    const int world = ctx->world, rank = ctx->rank;
+    std::string e;
+    if (!nccl_load(&e)) { ctx->err = e; g_create_error = e; return L2B_ERR_COMM; }
+    ncclUniqueId id;
+    memcpy(&id, shard->comm_id, sizeof id);
+    ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
+    if (r != ncclSuccess) {
+        ctx->err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r);
+        g_create_error = ctx->err;
+        return L2B_ERR_COMM;
+    }
+    const char *mode = getenv("L2B_TP");
+    const bool want = !(mode && strcmp(mode, "nccl") == 0);
+    int ok = want ? 1 : 0;
+    cudaIpcMemHandle_t hx{};
+    if (ok && cudaIpcGetMemHandle(&hx, ctx->arena) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+    }
+    // every rank learns every rank's handle (and whether it could make one) through NCCL
+    struct Msg { cudaIpcMemHandle_t hx; int ok; int pad[3]; };
+    static_assert(sizeof(Msg) % 16 == 0, "Msg must be 16-byte sized");
+    Msg mine{hx, ok, {0, 0, 0}};
+    Msg *d_all = nullptr;
+    L2B_TRY(dev_alloc(ctx, &d_all, (size_t)world));
+    L2B_TRY(cuda_try(ctx, cudaMemcpyAsync(d_all + rank, &mine, sizeof(Msg), cudaMemcpyHostToDevice, ctx->stream), "msg upload"));
+    if (g_nccl.AllGather(d_all + rank, d_all, sizeof(Msg), ncclChar, ctx->comm, ctx->stream) != ncclSuccess) {
+        ctx->err = "ncclAllGather(ipc handles) failed"; g_create_error = ctx->err; return L2B_ERR_COMM;
+    }
+    std::vector<Msg> all(world);
+    L2B_TRY(cuda_try(ctx, cudaMemcpyAsync(all.data(), d_all, sizeof(Msg) * world, cudaMemcpyDeviceToHost, ctx->stream), "msg download"));
+    L2B_TRY(cuda_try(ctx, cudaStreamSynchronize(ctx->stream), "ipc exchange"));
+    for (int q = 0; q < world; ++q) ok = ok && all[q].ok;
+    if (ok) {
+        for (int q = 0; q < world && ok; ++q) {
+            if (q == rank) continue;
+            void *px = nullptr;
+            if (cudaIpcOpenMemHandle(&px, all[q].hx, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+                break;
+            }
+            ctx->ipc_opened.push_back(px);
+            ctx->peer_arena[q] = (unsigned char *)px;
+        }
+    }
+    // all ranks must take the same path: agree through a max-reduce of the failure bit
+    int *d_bad = nullptr;
+    L2B_TRY(dev_alloc(ctx, &d_bad, (size_t)1));
+    int bad = ok ? 0 : 1;
+    L2B_TRY(cuda_try(ctx, cudaMemcpyAsync(d_bad, &bad, sizeof(int), cudaMemcpyHostToDevice, ctx->stream), "flag upload"));
+    if (g_nccl.AllReduce(d_bad, d_bad, 1, ncclInt, ncclMax, ctx->comm, ctx->stream) != ncclSuccess) {
+        ctx->err = "ncclAllReduce(ipc agreement) failed"; g_create_error = ctx->err; return L2B_ERR_COMM;
+    }
+    L2B_TRY(cuda_try(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "flag download"));
+    L2B_TRY(cuda_try(ctx, cudaStreamSynchronize(ctx->stream), "ipc agreement"));
+    ctx->use_p2p = (bad == 0);
+    return L2B_OK;
+}
+
+void destroy_rank(l2b_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    // graphs first: NCCL keeps a communicator alive (ncclCommDestroy spins) while captured
+    // graphs still reference it
+    for (int i = 0; i < G_COUNT; ++i)
+        if (ctx->graphs[i]) cudaGraphExecDestroy(ctx->graphs[i]);
+    cudaDeviceSynchronize();
+    if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
+    for (void *p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
+    for (void *p : ctx->owned) cudaFree(p);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
+        if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+    }
+    if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
+    if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
+    if (ctx->h_ints) cudaFreeHost(ctx->h_ints);
+    if (ctx->h_gen) cudaFreeHost(ctx->h_gen);
+    if (ctx->h_cand) cudaFreeHost(ctx->h_cand);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+void destroy_all(l2b_ctx *ctx) {
+    if (!ctx) return;
+    std::vector<l2b_ctx *> ranks = locals(ctx);
+    // every rank must be idle before any rank's memory (a peer's landing area) goes away
+    for (l2b_ctx *c : ranks) { cudaSetDevice(c->device); if (c->stream) cudaStreamSynchronize(c->stream); }
+    for (size_t i = ranks.size(); i-- > 0;) destroy_rank(ranks[i]);
+}
+
+int common_create(l2b_ctx **out, const l2b_config *cfg, const Source &src, uint64_t n_floats,
+                  const float *rope_cos, const float *rope_sin, const l2b_shard *shard, int n_gpus) {
+    if (!out || !cfg) { g_create_error = "NULL argument"; return L2B_ERR_INVALID_ARG; }
+    *out = nullptr;
+    const bool in_process = n_gpus > 1;
+    const int world = shard ? shard->world_size : n_gpus;
+    std::string why;
+    int rc = validate_config(cfg, world, &why);
+    if (rc) { g_create_error = why; return rc; }
+    if (shard && (shard->rank < 0 || shard->rank >= world)) { g_create_error = "rank out of range"; return L2B_ERR_INVALID_ARG; }
+    if (src.host && n_floats < checkpoint_floats(cfg)) {
+        g_create_error = "host_weights shorter than the checkpoint layout requires";
+        return L2B_ERR_INVALID_ARG;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_create_error = "no CUDA device";
+        return L2B_ERR_NO_DEVICE;
+    }
+    if (in_process && ndev < n_gpus) { g_create_error = "fewer CUDA devices than n_gpus"; return L2B_ERR_NO_DEVICE; }
+    const int device0 = shard ? shard->device : 0;
+    if (device0 < 0 || device0 >= ndev) { g_create_error = "device ordinal out of range"; return L2B_ERR_INVALID_ARG; }
+
+    std::vector<l2b_ctx *> ranks;
+    auto bail = [&](int code) {
+        for (size_t i = ranks.size(); i-- > 0;) destroy_rank(ranks[i]);
+        return code;
+    };
+    const int nlocal = in_process ? n_gpus : 1;
+    for (int i = 0; i < nlocal; ++i) {
+        l2b_ctx *ctx = new l2b_ctx();
+        ranks.push_back(ctx);
+        const int rank = in_process ? i : (shard ? shard->rank : 0);
+        const int device = in_process ? i : device0;
+        rc = create_rank(ctx, cfg, src, rope_cos, rope_sin, rank, world, device);
+        if (rc) return bail(rc);
+    }
+    if (in_process) {
+        // one process drives all GPUs: peers are plain UVA pointers once peer access is on
+        for (l2b_ctx *a : ranks) {
+            cudaSetDevice(a->device);
+            for (l2b_ctx *b : ranks) {
+                if (a == b) continue;
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, a->device, b->device);
+                if (!can) { g_create_error = "GPUs are not peer-accessible (NVLink/NVSwitch required for n_gpus > 1)"; return bail(L2B_ERR_COMM); }
+                cudaError_t e = cudaDeviceEnablePeerAccess(b->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { g_create_error = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return bail(L2B_ERR_COMM); }
+                cudaGetLastError();
+                a->peer_arena[b->rank] = b->arena;
+            }
+            a->use_p2p = true;
+            a->leader = ranks[0];
+        }
+    } else if (world > 1) {
+        rc = connect_ipc(ranks[0], shard);
+        if (rc) return bail(rc);
+    }
+    rc = warm_up(ranks);
+    if (rc) return bail(rc);
+    if (in_process) ranks[0]->members = ranks;
+    *out = ranks[0];
+    return L2B_OK;
+}
+#undef L2B_TRY
+
+// ---- running a call on every local rank -------------------------------------------------------
+void fill_ctl(l2b_ctx *ctx, int token, int pos, int stop_on_bos, float temperature, float top_p) {
+    int *h = ctx->h_ctl;
+    h[CTL_TOKEN] = token; h[CTL_POS] = pos; h[CTL_DONE] = 0; h[CTL_STEP] = 0;
+    h[CTL_STOP_ON_BOS] = stop_on_bos;
+    memcpy(&h[CTL_TEMP], &temperature, sizeof(float));
+    memcpy(&h[CTL_TOPP], &top_p, sizeof(float));
+}
+
+int finish_call(l2b_ctx *lead, const std::vector<l2b_ctx *> &ranks) {
+    int rc = L2B_OK;
+    for (l2b_ctx *c : ranks) {
+        cudaSetDevice(c->device);
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess && rc == L2B_OK) {
+            lead->err = std::string("step failed: ") + cudaGetErrorString(e);
+            rc = L2B_ERR_CUDA;
+        }
+        if (c->h_ctl[CTL_WORDS + CTL_ERR] && rc == L2B_OK) {
+            lead->err = "tensor-parallel exchange timed out: a peer rank died or fell out of lockstep";
+            rc = L2B_ERR_COMM;
+        }
+    }
+    return rc;
+}
+
+// run one step; which: G_LOGITS / G_ARGMAX_ONE / G_SAMPLE
+int run_step(l2b_ctx *lead, int token, int pos, int which, float temperature, float top_p) {
+    std::vector<l2b_ctx *> ranks = locals(lead);
+    for (l2b_ctx *ctx : ranks) {
+        L2B_CUDA(lead, cudaSetDevice(ctx->device));
+        fill_ctl(ctx, token, pos, 0, temperature, top_p);
+        ctx->last_launches = 0;
+        if (ctx == lead) L2B_CUDA(lead, cudaEventRecord(ctx->ev0, ctx->stream));
+        if (ctx->use_graphs) {
+            L2B_CUDA(lead, cudaGraphLaunch(ctx->graphs[which], ctx->stream));
+            ctx->last_launches = ctx->launches_per_step + (which == G_LOGITS ? 0 : 1);
+        } else {
+            int rc = enqueue_call(ctx, ctx->stream, which);
+            if (rc) { lead->err = ctx->err; return rc; }
+        }
+        if (ctx == lead) L2B_CUDA(lead, cudaEventRecord(ctx->ev1, ctx->stream));
+    }
+    int rc = finish_call(lead, ranks);
+    if (rc) return rc;
+    L2B_CUDA(lead, cudaSetDevice(lead->device));
+    L2B_CUDA(lead, cudaEventElapsedTime(&lead->last_ms, lead->ev0, lead->ev1));
+    if (pos + 1 > lead->n_appended) lead->n_appended = pos + 1;
     return L2B_OK;
 }
 
@@ -1112,12 +1312,12 @@ uint64_t l2b_checkpoint_floats(const l2b_config *cfg) { return cfg ? checkpoint_
 int32_t l2b_create(l2b_ctx **out, const l2b_config *cfg, const float *host_weights, uint64_t n_floats,
                    const float *rope_cos, const float *rope_sin, int32_t n_gpus) {
     if (!host_weights) { g_create_error = "host_weights is NULL"; return L2B_ERR_INVALID_ARG; }
-    if (n_gpus != 1) {
-        g_create_error = "l2b_create drives one GPU; use l2b_create_sharded (one process per GPU) for 2/4/8";
+    if (n_gpus != 1 && n_gpus != 2 && n_gpus != 4 && n_gpus != 8) {
+        g_create_error = "n_gpus must be 1, 2, 4 or 8";
         return L2B_ERR_UNSUPPORTED;
     }
     Source s; s.host = host_weights;
-    return common_create(out, cfg, s, n_floats, rope_cos, rope_sin, nullptr);
+    return common_create(out, cfg, s, n_floats, rope_cos, rope_sin, nullptr, n_gpus);
 }
 
 int32_t l2b_create_sharded(l2b_ctx **out, const l2b_config *cfg, const float *host_weights,
@@ -1125,34 +1325,24 @@ int32_t l2b_create_sharded(l2b_ctx **out, const l2b_config *cfg, const float *ho
                            const l2b_shard *shard) {
     if (!host_weights || !shard) { g_create_error = "NULL argument"; return L2B_ERR_INVALID_ARG; }
     Source s; s.host = host_weights;
-    return common_create(out, cfg, s, n_floats, rope_cos, rope_sin, shard);
+    return common_create(out, cfg, s, n_floats, rope_cos, rope_sin, shard, 1);
 }
 
 int32_t l2b_create_synthetic(l2b_ctx **out, const l2b_config *cfg, uint64_t seed, const l2b_shard *shard) {
     Source s; s.host = nullptr; s.seed = seed;
-    return common_create(out, cfg, s, 0, nullptr, nullptr, shard);
+    return common_create(out, cfg, s, 0, nullptr, nullptr, shard, 1);
 }
 
-void l2b_destroy(l2b_ctx *ctx) {
-    if (!ctx) return;
-    cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    // graphs first: NCCL keeps a communicator alive (ncclCommDestroy spins) while captured
-    // graphs still reference it
-    if (ctx->graph_logits) cudaGraphExecDestroy(ctx->graph_logits);
-    if (ctx->graph_argmax) cudaGraphExecDestroy(ctx->graph_argmax);
-    cudaDeviceSynchronize();
-    if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
-    for (void *p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
-    for (void *p : ctx->owned) cudaFree(p);
-    if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
-    if (ctx->h_ints) cudaFreeHost(ctx->h_ints);
-    if (ctx->h_gen) cudaFreeHost(ctx->h_gen);
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    delete ctx;
+int32_t l2b_create_synthetic_group(l2b_ctx **out, const l2b_config *cfg, uint64_t seed, int32_t n_gpus) {
+    if (n_gpus != 1 && n_gpus != 2 && n_gpus != 4 && n_gpus != 8) {
+        g_create_error = "n_gpus must be 1, 2, 4 or 8";
+        return L2B_ERR_UNSUPPORTED;
+    }
+    Source s; s.host = nullptr; s.seed = seed;
+    return common_create(out, cfg, s, 0, nullptr, nullptr, nullptr, n_gpus);
 }
+
+void l2b_destroy(l2b_ctx *ctx) { destroy_all(ctx); }
 
 int32_t l2b_reset(l2b_ctx *ctx) {
     if (!ctx) return L2B_ERR_INVALID_ARG;
@@ -1160,11 +1350,13 @@ int32_t l2b_reset(l2b_ctx *ctx) {
     return L2B_OK;
 }
 
+float *l2b_logits_buffer(l2b_ctx *ctx) { return ctx ? ctx->h_logits : nullptr; }
+
 int32_t l2b_forward_pinned(l2b_ctx *ctx, int32_t token, int32_t pos, const float **logits) {
     int rc = check_step_args(ctx, token, pos);
     if (rc) return rc;
     if (!logits) return fail(ctx, L2B_ERR_INVALID_ARG, "logits is NULL");
-    rc = run_step(ctx, token, pos, 0);
+    rc = run_step(ctx, token, pos, G_LOGITS, 1.0f, 0.0f);
     if (rc) return rc;
     *logits = ctx->h_logits;
     return L2B_OK;
@@ -1174,11 +1366,13 @@ int32_t l2b_forward(l2b_ctx *ctx, int32_t token, int32_t pos, float *host_logits
     int rc = check_step_args(ctx, token, pos);
     if (rc) return rc;
     if (!host_logits) return fail(ctx, L2B_ERR_INVALID_ARG, "host_logits is NULL");
-    rc = run_step(ctx, token, pos, 0);
+    rc = run_step(ctx, token, pos, G_LOGITS, 1.0f, 0.0f);
     if (rc) return rc;
-    // state.logits of the reference is one long-lived buffer (src/main.zig:149): copy with a
-    // streaming memcpy from the pinned landing buffer (the D2H DMA itself is part of the graph)
-    memcpy(host_logits, ctx->h_logits, (size_t)ctx->cfg.vocab_size * sizeof(float));
+    // state.logits of the reference is one long-lived buffer (src/main.zig:149).  A host that
+    // adopted l2b_logits_buffer() as that buffer gets the logits without a second copy; any other
+    // destination gets one streaming memcpy from the pinned landing buffer.
+    if (host_logits != ctx->h_logits)
+        memcpy(host_logits, ctx->h_logits, (size_t)ctx->cfg.vocab_size * sizeof(float));
     return L2B_OK;
 }
 
@@ -1186,9 +1380,32 @@ int32_t l2b_forward_argmax(l2b_ctx *ctx, int32_t token, int32_t pos, int32_t *ne
     int rc = check_step_args(ctx, token, pos);
     if (rc) return rc;
     if (!next) return fail(ctx, L2B_ERR_INVALID_ARG, "next is NULL");
-    rc = run_step(ctx, token, pos, 1);
+    rc = run_step(ctx, token, pos, G_ARGMAX_ONE, 1.0f, 0.0f);
     if (rc) return rc;
     *next = ctx->h_ints[0];
+    return L2B_OK;
+}
+
+int32_t l2b_forward_sample(l2b_ctx *ctx, int32_t token, int32_t pos, float temperature, float top_p,
+                           float *host_probs, l2b_prob_index *cand, int32_t cand_cap, int32_t *n_cand) {
+    int rc = check_step_args(ctx, token, pos);
+    if (rc) return rc;
+    if (!(temperature > 0.0f)) return fail(ctx, L2B_ERR_INVALID_ARG, "temperature must be > 0 (use l2b_forward_argmax for 0)");
+    if (top_p < 0.0f || top_p > 1.0f) return fail(ctx, L2B_ERR_INVALID_ARG, "top_p must be in [0, 1]");
+    const bool filter = (top_p != 0.0f && top_p != 1.0f);            // :1009
+    if (filter && (!cand || !n_cand || cand_cap <= 0)) return fail(ctx, L2B_ERR_INVALID_ARG, "candidate buffer missing");
+    rc = run_step(ctx, token, pos, G_SAMPLE, temperature, filter ? top_p : -1.0f);
+    if (rc) return rc;
+    const int V = ctx->cfg.vocab_size;
+    if (host_probs && host_probs != ctx->h_logits) memcpy(host_probs, ctx->h_logits, (size_t)V * sizeof(float));
+    if (n_cand) *n_cand = 0;
+    if (filter) {
+        const int n = ctx->h_ints[2];
+        if (n > kCandCap || n > cand_cap) { *n_cand = -n; return L2B_OK; }   // too many: filter host_probs on the host
+        static_assert(sizeof(l2b_prob_index) == sizeof(ProbIndex), "candidate layout");
+        memcpy(cand, ctx->h_cand, (size_t)n * sizeof(ProbIndex));
+        *n_cand = n;
+    }
     return L2B_OK;
 }
 
@@ -1201,44 +1418,50 @@ int32_t l2b_generate_argmax(l2b_ctx *ctx, int32_t token, int32_t pos, int32_t n_
     if (n_steps > ctx->cfg.seq_len - pos) n_steps = ctx->cfg.seq_len - pos;   // :992-993
     *n_done = 0;
     if (n_steps == 0) return L2B_OK;
-    L2B_CUDA(ctx, cudaSetDevice(ctx->device));
-    // forced tokens (prompt forcing, :999-1000); -1 = free-running
-    for (int i = 0; i < n_steps; ++i) ctx->h_gen[i] = forced ? forced[i] : -1;
-    L2B_CUDA(ctx, cudaMemcpyAsync(ctx->gen_forced, ctx->h_gen, (size_t)n_steps * sizeof(int),
-                                  cudaMemcpyHostToDevice, ctx->stream));
-    L2B_CUDA(ctx, cudaMemsetAsync(ctx->gen_ndone, 0, sizeof(int), ctx->stream));
-    ctx->last_launches = 0;
-    L2B_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    set_ctl_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, token, pos, stop_on_bos ? 1 : 0, ctx->amax);
-    L2B_CUDA(ctx, cudaGetLastError());
-    int launches = 1;
+    std::vector<l2b_ctx *> ranks = locals(ctx);
+    int launches = 0;
+    for (l2b_ctx *c : ranks) {
+        L2B_CUDA(ctx, cudaSetDevice(c->device));
+        // forced tokens (prompt forcing, :999-1000); -1 = free-running
+        for (int i = 0; i < n_steps; ++i) c->h_gen[i] = forced ? forced[i] : -1;
+        L2B_CUDA(ctx, cudaMemcpyAsync(c->gen_forced, c->h_gen, (size_t)n_steps * sizeof(int),
+                                      cudaMemcpyHostToDevice, c->stream));
+        L2B_CUDA(ctx, cudaMemsetAsync(c->gen_ndone, 0, sizeof(int), c->stream));
+        L2B_CUDA(ctx, cudaMemsetAsync(c->amax, 0, sizeof(unsigned long long), c->stream));
+        fill_ctl(c, token, pos, stop_on_bos ? 1 : 0, 1.0f, -1.0f);
+        if (c == ctx) L2B_CUDA(ctx, cudaEventRecord(c->ev0, c->stream));
+        L2B_CUDA(ctx, cudaMemcpyAsync(c->ctl, c->h_ctl, CTL_HOST_WORDS * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+    // the whole step depends on (token,pos) only through ctl, which advance_kernel updates, so the
+    // same graph is replayed back to back with no host round trip; with several local ranks the
+    // launches are interleaved so that no rank's queue runs dry while another's is being filled
     for (int i = 0; i < n_steps; ++i) {
-        // the whole step depends on (token,pos) only through ctl, which advance_kernel updates,
-        // so the same graph is replayed back to back with no host round trip
-        if (ctx->use_mega) {
-            ctx->last_launches = 0;
-            rc = enqueue_mega_step(ctx, ctx->stream, true, true);
-            if (rc) return rc;
-            launches += ctx->last_launches;
-        } else if (ctx->use_graphs) {
-            L2B_CUDA(ctx, cudaGraphLaunch(ctx->graph_argmax, ctx->stream));
-            launches += ctx->launches_per_step + 1;
-        } else {
-            ctx->last_launches = 0;
-            rc = enqueue_step(ctx, ctx->stream, true);
-            if (rc) return rc;
-            advance_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, ctx->amax, ctx->gen_forced, ctx->gen_out,
-                                                     ctx->gen_ndone);
-            L2B_CUDA(ctx, cudaGetLastError());
-            launches += ctx->last_launches + 1;
+        for (l2b_ctx *c : ranks) {
+            if (ranks.size() > 1) L2B_CUDA(ctx, cudaSetDevice(c->device));
+            if (c->use_graphs) {
+                L2B_CUDA(ctx, cudaGraphLaunch(c->graphs[G_ARGMAX_LOOP], c->stream));
+                if (c == ctx) launches += c->launches_per_step + 1;
+            } else {
+                c->last_launches = 0;
+                rc = enqueue_call(c, c->stream, G_ARGMAX_LOOP);
+                if (rc) { ctx->err = c->err; return rc; }
+                if (c == ctx) launches += c->last_launches;
+            }
         }
     }
-    L2B_CUDA(ctx, cudaMemcpyAsync(ctx->h_gen, ctx->gen_out, (size_t)n_steps * sizeof(int),
-                                  cudaMemcpyDeviceToHost, ctx->stream));
-    L2B_CUDA(ctx, cudaMemcpyAsync(ctx->h_ints + 1, ctx->gen_ndone, sizeof(int), cudaMemcpyDeviceToHost,
-                                  ctx->stream));
-    L2B_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    L2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (l2b_ctx *c : ranks) {
+        L2B_CUDA(ctx, cudaSetDevice(c->device));
+        if (c == ctx) {
+            L2B_CUDA(ctx, cudaMemcpyAsync(c->h_gen, c->gen_out, (size_t)n_steps * sizeof(int),
+                                          cudaMemcpyDeviceToHost, c->stream));
+            L2B_CUDA(ctx, cudaMemcpyAsync(c->h_ints + 1, c->gen_ndone, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        }
+        L2B_CUDA(ctx, cudaMemcpyAsync(c->h_ctl + CTL_WORDS, c->ctl, CTL_WORDS * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        if (c == ctx) L2B_CUDA(ctx, cudaEventRecord(c->ev1, c->stream));
+    }
+    rc = finish_call(ctx, ranks);
+    if (rc) return rc;
+    L2B_CUDA(ctx, cudaSetDevice(ctx->device));
     L2B_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     const int done = ctx->h_ints[1];
     for (int i = 0; i < done; ++i) out_next[i] = ctx->h_gen[i];
@@ -1254,7 +1477,7 @@ int32_t l2b_read_state(l2b_ctx *ctx, int32_t which, float *dst, uint64_t n, uint
     uint64_t cnt = 0;
     const uint64_t L = ctx->cfg.n_layers, S = ctx->cfg.seq_len;
     switch (which) {
-    case 0: src = ctx->X[ctx->final_x]; cnt = ctx->dim; break;
+    case 0: src = ctx->X; cnt = ctx->dim; break;
     case 1: src = ctx->xb; cnt = ctx->q_loc; break;
     case 2: src = ctx->hb; cnt = ctx->hid_loc; break;
     case 3: src = ctx->q; cnt = ctx->q_loc; break;
@@ -1277,30 +1500,45 @@ int32_t l2b_last_timing(const l2b_ctx *ctx, float *device_ms, int32_t *kernel_la
     return L2B_OK;
 }
 
+int32_t l2b_load_stats(const l2b_ctx *ctx, double *upload_ms, uint64_t *upload_bytes) {
+    if (!ctx) return L2B_ERR_INVALID_ARG;
+    if (upload_ms) *upload_ms = ctx->load_ms;
+    if (upload_bytes) *upload_bytes = ctx->load_bytes;
+    return L2B_OK;
+}
+
 int32_t l2b_profile_step(l2b_ctx *ctx, int32_t token, int32_t pos, l2b_kernel_time *out, int32_t cap,
                          int32_t *n_out) {
     int rc = check_step_args(ctx, token, pos);
     if (rc) return rc;
     if (!out || !n_out || cap <= 0) return fail(ctx, L2B_ERR_INVALID_ARG, "bad profile arguments");
-    L2B_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<l2b_ctx *> ranks = locals(ctx);
     if (pos + 1 > ctx->n_appended) ctx->n_appended = pos + 1;   // attention bytes use this
     const int saved_appended = ctx->n_appended;
-    ctx->n_appended = pos + 1;
-    set_ctl_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, token, pos, 0, ctx->amax);
-    L2B_CUDA(ctx, cudaGetLastError());
-    ctx->profiling = true;
-    ctx->prof_ev.clear();
-    ctx->prof_rec.clear();
-    rc = enqueue_step(ctx, ctx->stream, false);
-    ctx->profiling = false;
-    ctx->n_appended = saved_appended;
     cudaEvent_t last = nullptr;
-    if (rc == L2B_OK) {
-        if (cudaEventCreate(&last) != cudaSuccess || cudaEventRecord(last, ctx->stream) != cudaSuccess)
-            rc = fail(ctx, L2B_ERR_CUDA, "event record failed");
+    for (l2b_ctx *c : ranks) {
+        L2B_CUDA(ctx, cudaSetDevice(c->device));
+        c->n_appended = pos + 1;
+        fill_ctl(c, token, pos, 0, 1.0f, -1.0f);
+        L2B_CUDA(ctx, cudaMemcpyAsync(c->ctl, c->h_ctl, CTL_HOST_WORDS * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        c->profiling = (c == ctx);
+        c->prof_ev.clear();
+        c->prof_rec.clear();
+        int r2 = enqueue_step(c, c->stream, MODE_LOGITS);
+        c->profiling = false;
+        if (r2 && rc == L2B_OK) { rc = r2; ctx->err = c->err; }
+        if (c == ctx && rc == L2B_OK) {
+            if (cudaEventCreate(&last) != cudaSuccess || cudaEventRecord(last, c->stream) != cudaSuccess)
+                rc = fail(ctx, L2B_ERR_CUDA, "event record failed");
+        }
+        cudaMemcpyAsync(c->h_ctl + CTL_WORDS, c->ctl, CTL_WORDS * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
     }
-    if (rc == L2B_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
-        rc = fail(ctx, L2B_ERR_CUDA, "profile step failed");
+    ctx->n_appended = saved_appended;
+    {
+        int r2 = finish_call(ctx, ranks);
+        if (rc == L2B_OK) rc = r2;
+    }
+    cudaSetDevice(ctx->device);
     const int n = (int)ctx->prof_rec.size();
     if (rc == L2B_OK) {
         for (int i = 0; i < n; ++i) {
@@ -1324,6 +1562,7 @@ int32_t l2b_debug_trace(l2b_ctx *ctx, unsigned long long *dst, uint64_t cap_word
     if (!ctx->trace) return fail(ctx, L2B_ERR_STATE, "tracing not enabled (L2B_TRACE=1)");
     const uint64_t n = (uint64_t)ctx->trace_launches * TRACE_MAX_CTAS * TRACE_SLOTS;
     if (cap_words < n) return fail(ctx, L2B_ERR_INVALID_ARG, "dst too small");
+    L2B_CUDA(ctx, cudaSetDevice(ctx->device));
     L2B_CUDA(ctx, cudaMemcpy(dst, ctx->trace, n * 8, cudaMemcpyDeviceToHost));
     if (n_words) *n_words = n;
     return L2B_OK;
@@ -1422,27 +1661,40 @@ struct OpScope {
 };
 }  // namespace
 
-int32_t l2b_op_matmul(int32_t device, float *xout, const float *x, const float *w, int32_t d, int32_t n) {
-    if (!xout || !x || !w || d <= 0 || n <= 0) return L2B_ERR_INVALID_ARG;   // asserts :534-536
+// W . rmsnorm(x, gamma) (gamma NULL => W . x), optionally accumulated into resid_inout, through a
+// chosen GEMV kernel flavour: the fused prologue / residual epilogue of the hot path in isolation
+int32_t l2b_op_fused_matmul(int32_t device, float *xout, const float *x, const float *gamma, const float *w,
+                            float *resid_inout, int32_t d, int32_t n, int32_t kernel) {
+    if ((!xout && !resid_inout) || !x || !w || d <= 0 || n <= 0 || kernel < 0 || kernel > 3) return L2B_ERR_INVALID_ARG;
+    if (n % 4) { g_create_error = "n must be a multiple of 4"; return L2B_ERR_UNSUPPORTED; }
     OpScope s(device);
-    float *dx = s.up(x, n), *dw = s.up(w, (size_t)d * n), *dout = s.up(nullptr, d);
+    float *dx = s.up(x, n), *dw = s.up(w, (size_t)d * n), *dg = gamma ? s.up(gamma, n) : nullptr;
+    float *dout = s.up(resid_inout ? resid_inout : nullptr, d);
     int *ctl = (int *)s.up(nullptr, CTL_WORDS);
     if (s.rc) return s.rc;
     cudaMemset(ctl, 0, CTL_WORDS * sizeof(int));
-    if (n % 4 == 0) {
-        l2b_ctx tmp;   // only for launch_gemv's bookkeeping
-        tmp.device = device;
-        cudaDeviceProp prop{};
-        cudaGetDeviceProperties(&prop, device);
-        tmp.num_sms = prop.multiProcessorCount;
-        GemvParams p{};
-        p.ctl = ctl; p.n = n; p.x_in = dx; p.w0 = dw; p.total_rows = d; p.rows0 = d; p.out0 = dout;
-        int rc = launch_gemv(&tmp, EPI_STORE, p, 0);
-        if (rc) { g_create_error = tmp.err; return rc; }
-    } else {
-        int blocks = (d + NWARP - 1) / NWARP;
-        gemv_scalar_kernel<<<blocks, NT>>>(dout, dx, dw, d, n);
-    }
+    l2b_ctx tmp;   // only for launch_gemv's bookkeeping
+    tmp.device = device;
+    tmp.force_kernel = kernel;
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, device);
+    tmp.num_sms = prop.multiProcessorCount;
+    GemvParams p{};
+    p.ctl = ctl; p.n = n; p.x_in = dx; p.gamma = dg; p.w0 = dw; p.total_rows = d; p.rows0 = d; p.out0 = dout;
+    int rc = launch_gemv(&tmp, resid_inout ? EPI_RESID : EPI_STORE, p, 0);
+    if (rc) { g_create_error = tmp.err; return rc; }
+    s.down(resid_inout ? resid_inout : xout, dout, d);
+    return s.rc;
+}
+
+int32_t l2b_op_matmul(int32_t device, float *xout, const float *x, const float *w, int32_t d, int32_t n) {
+    if (!xout || !x || !w || d <= 0 || n <= 0) return L2B_ERR_INVALID_ARG;   // asserts :534-536
+    if (n % 4 == 0) return l2b_op_fused_matmul(device, xout, x, nullptr, w, nullptr, d, n, 0);
+    OpScope s(device);
+    float *dx = s.up(x, n), *dw = s.up(w, (size_t)d * n), *dout = s.up(nullptr, d);
+    if (s.rc) return s.rc;
+    int blocks = (d + NWARP - 1) / NWARP;
+    gemv_scalar_kernel<<<blocks, NT>>>(dout, dx, dw, d, n);
     s.down(xout, dout, d);
     return s.rc;
 }
@@ -1484,7 +1736,7 @@ int32_t l2b_op_attention_head(int32_t device, float *out, const float *q, const 
                               const float *values, int32_t head_size, int32_t kv_stride, int32_t n_pos) {
     if (!out || !q || !keys || !values || head_size <= 0 || n_pos <= 0 || kv_stride < head_size)
         return L2B_ERR_INVALID_ARG;
-    if (head_size % 4 || kv_stride % 4 || head_size / 4 > NT) { g_create_error = "head_size/kv_stride must be multiples of 4"; return L2B_ERR_UNSUPPORTED; }
+    if (head_size % 4 || kv_stride % 4 || head_size > NT) { g_create_error = "head_size/kv_stride must be multiples of 4 and head_size <= 256"; return L2B_ERR_UNSUPPORTED; }
     OpScope s(device);
     const size_t nkv = (size_t)n_pos * kv_stride;
     float *dq = s.up(q, head_size), *dk = s.up(keys, nkv), *dv = s.up(values, nkv), *dout = s.up(nullptr, head_size);
@@ -1493,7 +1745,7 @@ int32_t l2b_op_attention_head(int32_t device, float *out, const float *q, const 
     unsigned int *cnt = (unsigned int *)s.up(nullptr, 1);
     int *ctl = (int *)s.up(nullptr, CTL_WORDS);
     if (s.rc) return s.rc;
-    int hctl[CTL_WORDS] = {0, n_pos - 1, 0, 0, 0, 0, 0, 0};
+    int hctl[CTL_WORDS] = {0, n_pos - 1};
     cudaMemcpy(ctl, hctl, sizeof hctl, cudaMemcpyHostToDevice);
     cudaMemset(cnt, 0, sizeof(unsigned int));
     AttnParams a{};
@@ -1513,6 +1765,36 @@ int32_t l2b_op_attention_head(int32_t device, float *out, const float *q, const 
         fn<<<dim3(1, nsplit), NT, smem2>>>(a);
     }
     s.down(out, dout, head_size);
+    return s.rc;
+}
+
+// sampler preparation alone (src/main.zig:1005-1008, :761-768) on host logits: unit-test surface
+int32_t l2b_op_sample_prep(int32_t device, float *logits_inout, int32_t n, float temperature, float top_p,
+                           l2b_prob_index *cand, int32_t cand_cap, int32_t *n_cand) {
+    if (!logits_inout || n <= 1 || !(temperature > 0.0f) || !n_cand) return L2B_ERR_INVALID_ARG;
+    OpScope s(device);
+    float *dl = s.up(logits_inout, n);
+    int *ctl = (int *)s.up(nullptr, CTL_WORDS);
+    ProbIndex *dc = (ProbIndex *)s.up(nullptr, (size_t)2 * (cand_cap > 0 ? cand_cap : 1));
+    int *dn = (int *)s.up(nullptr, 1);
+    if (s.rc) return s.rc;
+    const bool filter = (top_p != 0.0f && top_p != 1.0f);
+    const float tp = filter ? top_p : -1.0f;
+    int hctl[CTL_WORDS] = {0};
+    memcpy(&hctl[CTL_TEMP], &temperature, sizeof(float));
+    memcpy(&hctl[CTL_TOPP], &tp, sizeof(float));
+    cudaMemcpy(ctl, hctl, sizeof hctl, cudaMemcpyHostToDevice);
+    cudaMemset(dn, 0, sizeof(int));
+    sample_prep_kernel<<<1, SAMP_THREADS>>>(dl, n, ctl, dc, cand_cap, dn);
+    s.down(logits_inout, dl, n);
+    if (s.rc) return s.rc;
+    int hn = 0;
+    cudaMemcpy(&hn, dn, sizeof(int), cudaMemcpyDeviceToHost);
+    *n_cand = hn;
+    if (filter && cand && hn > 0) {
+        const int m = hn < cand_cap ? hn : cand_cap;
+        cudaMemcpy(cand, dc, (size_t)m * sizeof(ProbIndex), cudaMemcpyDeviceToHost);
+    }
     return s.rc;
 }
 

@@ -224,7 +224,12 @@ extern "C" int32_t l2h_generate(l2b_ctx *ctx, const l2b_config *cfg, const l2h_g
     using clk = std::chrono::steady_clock;
     memset(res, 0, sizeof *res);
     const int V = cfg->vocab_size;
-    std::vector<float> logits(V);                                 // state.logits (:149)
+    // state.logits (:149).  The patched Zig host points state.logits at the library's pinned logits
+    // buffer, so the D2H DMA of every step lands in it and no second copy is made.
+    std::vector<float> own_logits;
+    float *logits_p = l2b_logits_buffer(ctx);
+    if (!logits_p) { own_logits.resize(V); logits_p = own_logits.data(); }
+    struct { float *p; float *data() const { return p; } float &operator[](int i) const { return p[i]; } } logits{logits_p};
     std::vector<IndexedF32> indexed(V);                           // state.logits_indexed (:150)
     int seq_len = opt->n_steps == 0 ? cfg->seq_len : opt->n_steps;   // :992
     seq_len = std::max(1, std::min(seq_len, cfg->seq_len));          // :993

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--shape", default="512,1376,3,8,8,-1024,96")
     ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--seed", type=int, default=5)
+    ap.add_argument("--dead-peer", action="store_true",
+                    help="rank 1 stops stepping: rank 0 must get L2B_ERR_COMM (-6), not hang")
     args = ap.parse_args()
     import llama2_zig_b200 as l2b
     from llama2_zig_b200.checkpoint import shape_checkpoint
@@ -46,6 +48,20 @@ def main():
         return bytes(idt.cpu().numpy().tobytes())
 
     tp = l2b.Transformer(ck, rank=rank, world_size=world, device=local, comm_id=fresh_id())
+    if args.dead_peer:
+        tp.forward(1, 0)                       # one good step on every rank
+        dist.barrier()
+        status = 0
+        if rank == 0:
+            try:
+                tp.forward(2, 1)               # rank 1 never makes this call
+            except l2b.L2BError as e:
+                status = e.status
+            print("DEAD_PEER_OK" if status == -6 else f"DEAD_PEER_FAIL status={status}", flush=True)
+        dist.barrier()
+        tp.close()
+        dist.destroy_process_group()
+        sys.exit(0 if (rank != 0 or status == -6) else 1)
     tp_syn = l2b.Transformer(shape_checkpoint(shape), synthetic_seed=args.seed, rank=rank, world_size=world,
                              device=local, comm_id=fresh_id())
     single = oracle = None
@@ -72,6 +88,24 @@ def main():
             if nxt != int(np.argmax(got)):
                 ok = False
                 print(f"device argmax {nxt} != argmax of gathered logits {int(np.argmax(got))} at pos {pos}", flush=True)
+    # the on-device generation loop (argmax exchanged between ranks inside advance_kernel)
+    tp.reset()
+    gen = tp.generate_argmax(1, 0, min(16, ck.seq_len), stop_on_bos=False)
+    if rank == 0:
+        single.reset()
+        gen1 = single.generate_argmax(1, 0, min(16, ck.seq_len), stop_on_bos=False)
+        if gen.tolist() != gen1.tolist():
+            ok = False
+            print(f"generate_argmax differs: tp {gen.tolist()} vs 1 GPU {gen1.tolist()}", flush=True)
+    # temperature sampling preparation on the device under TP (logits gathered from all ranks)
+    tp.reset()
+    probs, cand = tp.forward_sample(1, 0, 0.8, 0.9)
+    if rank == 0:
+        single.reset()
+        p1, c1 = single.forward_sample(1, 0, 0.8, 0.9)
+        if float(np.max(np.abs(probs - p1))) > 1e-4 * float(np.max(p1)) or (cand is None) != (c1 is None):
+            ok = False
+            print("forward_sample differs between tp and 1 GPU", flush=True)
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     if rank == 0:

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol(l2b):
     for n in names:
         assert n in defined, f"{n} declared in llama2_b200.h but not exported"
         assert hasattr(lib, n)
-    assert lib.l2b_abi_version() == 1
+    assert lib.l2b_abi_version() == 2
 
 
 def test_library_is_sm100a_only(l2b):
@@ -42,8 +42,14 @@ def test_create_rejects_bad_arguments_before_touching_cuda(l2b):
     data = np.zeros(8, np.float32)
     # NULL weights
     assert lib.l2b_create(C.byref(h), C.byref(cfg), None, 0, None, None, 1) == -1
-    # multi-GPU through the single-process entry point is refused, not silently ignored
-    assert lib.l2b_create(C.byref(h), C.byref(cfg), data.ctypes.data_as(FP), 8, None, None, 2) == -2
+    # n_gpus must be 1, 2, 4 or 8, and the shape must shard over it (6 kv heads % 4)
+    assert lib.l2b_create(C.byref(h), C.byref(cfg), data.ctypes.data_as(FP), 8, None, None, 3) == -2
+    assert lib.l2b_create(C.byref(h), C.byref(cfg), data.ctypes.data_as(FP), 8, None, None, 4) == -2
+    assert b"n_kv_heads" in lib.l2b_last_error(None)
+    # head_size > 256: the attention kernels write one output element per thread
+    wide = L2BConfig(1024, 2048, 2, 2, 2, 1000, 64, 1)
+    assert lib.l2b_create(C.byref(h), C.byref(wide), data.ctypes.data_as(FP), 8, None, None, 1) == -2
+    assert b"head_size" in lib.l2b_last_error(None)
     # unsupported shapes (head_size not a multiple of 4; dim not divisible by heads)
     bad = L2BConfig(36, 768, 6, 6, 6, 32000, 256, 1)
     assert lib.l2b_create(C.byref(h), C.byref(bad), data.ctypes.data_as(FP), 8, None, None, 1) == -2
