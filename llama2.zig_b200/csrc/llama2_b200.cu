@@ -146,7 +146,9 @@ struct l2b_ctx {
     int tma_ctas_per_sm = 1;
     int tma_stages = 0;                      // 0 = auto; else forced ring depth
     bool big_kernel_tma = true;              // bandwidth-bound GEMVs: TMA-ring kernel (false: register-fed 8-row kernel)
-    long long gemv8_min_bytes = 8ll << 20;   // >= this many weight bytes (and n >= 512): streaming kernel; -1 = never
+    long long gemv8_min_bytes = 8ll << 20;   // >= this many weight bytes (and n >= big_min_n): streaming kernel; -1 = never
+    int big_min_n = 1024;                    // measured r02: at n = 768 the TMA ring (192 of 256 columns per stage) loses to the latency kernel
+    int tpr_min_tiles_per_sm = 0;            // > 0: shrink threads-per-row while the grid still has this many tiles per SM (L2B_TPR_TILES)
     int force_kernel = 0;                    // l2b_op_fused_matmul: 0 auto, 1 small, 2 register-fed 8-row, 3 TMA ring
     int launches_per_step = 0;
     std::set<const void *> attr_done;        // kernels whose max-dynamic-smem attribute is set on this device
@@ -435,7 +437,7 @@ int launch_gemv(l2b_ctx *ctx, int epi, const GemvParams &p, cudaStream_t st, con
     const size_t xbytes = (size_t)p.n * 4 * (1 + (p.gamma ? 1 : 0));
     // bandwidth-bound shapes take the TMA-ring kernel (or the register-fed 8-row kernel when
     // L2B_GEMV_BIG=ldg), latency-bound ones the fine-grained kernel
-    bool big = ctx->gemv8_min_bytes >= 0 && p.n >= 512 &&
+    bool big = ctx->gemv8_min_bytes >= 0 && p.n >= ctx->big_min_n &&
                (uint64_t)p.total_rows * p.n * 4ull >= (uint64_t)ctx->gemv8_min_bytes;
     if (ctx->force_kernel == 1) big = false;
     if (ctx->force_kernel >= 2) big = true;
@@ -453,7 +455,12 @@ int launch_gemv(l2b_ctx *ctx, int epi, const GemvParams &p, cudaStream_t st, con
     if (ctx->force_kernel == 3 && !tma) return fail(ctx, L2B_ERR_UNSUPPORTED, "shape does not fit the TMA-ring kernel");
     const size_t smem = tma ? (size_t)nstage * stage_bytes + xonly : xbytes;
     if (smem > (size_t)kMaxSmemOptin) return fail(ctx, L2B_ERR_UNSUPPORTED, "activation vector too large for shared memory");
-    const int tpr = gemv_tpr(p.n);
+    int tpr = gemv_tpr(p.n);
+    // many-row matrices (the classifier): fewer threads per row = more 128-bit loads in flight per
+    // thread and fewer shuffle steps per row, as long as the grid still covers the SMs
+    while (ctx->tpr_min_tiles_per_sm > 0 && tpr > 8 &&
+           (p.total_rows + (NT / (tpr / 2)) * GEMV_R - 1) / ((NT / (tpr / 2)) * GEMV_R) >= ctx->tpr_min_tiles_per_sm * ctx->num_sms)
+        tpr /= 2;
     gemv_fn fn = tma ? gemv_tma_pick(epi) : big ? gemv8_pick(epi) : gemv_pick(epi, tpr);
     if (!ctx->attr_done.count((const void *)fn)) {
         L2B_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
@@ -840,6 +847,26 @@ int cuda_try(l2b_ctx *ctx, cudaError_t e, const char *what) {
     return e == cudaErrorMemoryAllocation ? L2B_ERR_OOM : L2B_ERR_CUDA;
 }
 
+// Load every kernel this library can launch onto the current device NOW.  With CUDA's default lazy
+// module loading a kernel is loaded at its first launch, which can need the device to go idle —
+// and a tensor-parallel kernel that is spinning on a peer (which the same host thread has not
+// launched yet, in-process groups) would then never let it.
+int preload_kernels(l2b_ctx *ctx) {
+    cudaFuncAttributes fa;
+    const int tprs[] = {8, 16, 32, 64, 128, 256};
+    for (int epi = 0; epi < EPI_COUNT; ++epi) {
+        for (int tpr : tprs) L2B_CUDA(ctx, cudaFuncGetAttributes(&fa, (const void *)gemv_pick(epi, tpr)));
+        L2B_CUDA(ctx, cudaFuncGetAttributes(&fa, (const void *)gemv8_pick(epi)));
+        L2B_CUDA(ctx, cudaFuncGetAttributes(&fa, (const void *)gemv_tma_pick(epi)));
+    }
+    size_t smem = 0;
+    L2B_CUDA(ctx, cudaFuncGetAttributes(&fa, (const void *)pick_attention(ctx->head_size, true, &smem)));
+    const void *others[] = {(const void *)attention_kernel, (const void *)advance_kernel, (const void *)gather_logits_kernel,
+                            (const void *)resid_add_kernel, (const void *)sample_prep_kernel, (const void *)synth_fill_kernel};
+    for (const void *f : others) L2B_CUDA(ctx, cudaFuncGetAttributes(&fa, f));
+    return L2B_OK;
+}
+
 // ---- creation, stage 1: weights + run state of one rank (no peer is touched) ------------------
 int create_rank(l2b_ctx *ctx, const l2b_config *cfg, const Source &src, const float *rope_cos,
                 const float *rope_sin, int rank, int world, int device) {
@@ -863,6 +890,7 @@ int create_rank(l2b_ctx *ctx, const l2b_config *cfg, const Source &src, const fl
     L2B_TRY(cuda_try(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate"));
     L2B_TRY(cuda_try(ctx, cudaEventCreate(&ctx->ev0), "cudaEventCreate"));
     L2B_TRY(cuda_try(ctx, cudaEventCreate(&ctx->ev1), "cudaEventCreate"));
+    L2B_TRY(preload_kernels(ctx));
 
     const uint64_t dim = cfg->dim, hid = cfg->hidden_dim, L = cfg->n_layers, V = cfg->vocab_size, S = cfg->seq_len;
     const uint64_t hs = ctx->head_size, kvd = ctx->kv_dim;
@@ -1024,6 +1052,10 @@ int create_rank(l2b_ctx *ctx, const l2b_config *cfg, const Source &src, const fl
             L2B_TRY(dev_alloc(ctx, &ctx->trace, (size_t)ctx->trace_launches * TRACE_MAX_CTAS * TRACE_SLOTS));
             L2B_TRY(cuda_try(ctx, cudaMemset(ctx->trace, 0, (size_t)ctx->trace_launches * TRACE_MAX_CTAS * TRACE_SLOTS * 8), "memset"));
         }
+        const char *envn = getenv("L2B_BIG_MIN_N");
+        if (envn && atoi(envn) >= 4) ctx->big_min_n = atoi(envn);
+        const char *envp = getenv("L2B_TPR_TILES");
+        if (envp) ctx->tpr_min_tiles_per_sm = atoi(envp);
         const char *env6 = getenv("L2B_TMA_CTAS");
         if (env6) ctx->tma_ctas_per_sm = atoi(env6) > 0 ? atoi(env6) : 1;
     }

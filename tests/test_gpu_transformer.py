@@ -278,8 +278,14 @@ def test_forward_sample_matches_host_sampler_steps(l2b, oracle, stories15m):
             nxt = int(np.argmax(want))
             if temp != 1.0:
                 want = (want / np.float32(temp)).astype(np.float32)
+            ref64 = np.exp(want.astype(np.float64) - want.max())
+            ref64 /= ref64.sum()
             lib.orc_softmax(want.ctypes.data_as(FP), want.size)
-            assert np.max(np.abs(probs - want)) <= 1e-4 * np.max(want)
+            # the reference sums the 32000 exponentials sequentially in fp32 (:697-701): that sum itself is
+            # only good to ~1e-4, the device's tree sum to ~1e-7, so the bar against the restatement is
+            # 3e-4 and the bar against the exact softmax is the north star's 1e-4
+            assert np.max(np.abs(probs - want)) <= 3e-4 * np.max(want)
+            assert np.max(np.abs(probs - ref64)) <= 1e-4 * np.max(ref64)
             assert int(np.argmax(probs)) == nxt
             if top_p in (0.0, 1.0):
                 assert cand is None
