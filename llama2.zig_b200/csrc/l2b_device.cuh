@@ -8,6 +8,7 @@
 // warp-shuffle reductions.
 #pragma once
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -240,7 +241,10 @@ struct GemvParams {
     const float *x_in;      // n floats; when emb != nullptr: row `token` of emb is used instead
     const float *emb;       // token embedding table (layer 0: x = emb[token], :295-296) or nullptr
     const float *gamma;     // rmsnorm gain (n floats) => fused rmsnorm, or nullptr => plain staging
-    float *x_out;           // layer 0 only: CTA 0 copies the embedding row here (it becomes the residual stream)
+    float *x_out;           // CTA 0 writes the staged (un-normalised) x here: layer 0 (x = embedding row) and
+                            // kernels that fold `parts` in (x_out must then differ from x_in)
+    const float *parts;     // small-model fusion: nparts partial vectors [nparts][n] whose fixed-order sum is the
+    int nparts;             // pending residual (the wo / w2 result split by head / by hidden slice), or nullptr
     const int *ctl;         // control block (token, pos, done, epoch, error)
     int n;                  // columns (multiple of 4)
     // ---- matrices (virtual row space depends on the epilogue)
@@ -293,8 +297,13 @@ __device__ __forceinline__ const float *gemv_row_ptr(const GemvParams &p, int v)
 // the LL units of that slice (they arrive straight from the producers' epilogues over NVLink),
 // writes the new x slice and bumps `rdone`.  Every CTA then waits until all slices of this step are
 // done, so the 148 CTAs read 16 KB of finished x instead of 148 x g x 16 KB of partials.
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 constexpr int TP_SLICE4 = 32;
-__device__ __forceinline__ void tp_reduce_into_x(const GemvParams &p) {
+// bar_id / bar_threads: the barrier every caller passes through at the end (0, blockDim for the
+// block-structured kernels; the TMA kernel's prologue runs without its producer warp)
+__device__ __forceinline__ void tp_reduce_into_x(const GemvParams &p, int bar_id, int bar_threads) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int n4 = p.n >> 2;
     const int nslices = (n4 + TP_SLICE4 - 1) / TP_SLICE4;
@@ -330,7 +339,7 @@ __device__ __forceinline__ void tp_reduce_into_x(const GemvParams &p) {
             fence_proxy_async_global();   // x is about to be read through the TMA (async proxy)
         }
     }
-    __syncthreads();
+    named_bar_sync(bar_id, bar_threads);
 }
 
 // ---- shared prologue: stage the activation vector (+ rmsnorm) into shared memory.
@@ -339,22 +348,41 @@ __device__ __forceinline__ void gemv_stage_input(const GemvParams &p, float *xs,
                                                  uint64_t *bar, float *scratch) {
     const int tid = threadIdx.x;
     const int n4 = p.n >> 2;
-    if (p.ll_in) tp_reduce_into_x(p);
+    if (p.ll_in) tp_reduce_into_x(p, 0, NT);
     const float *xsrc = p.emb ? p.emb + (size_t)p.ctl[CTL_TOKEN] * p.n : p.x_in;
     float *gs = aux;
+    float *ps = p.gamma ? aux + p.n : aux;               // sum of the partial vectors (when p.parts)
     if (tid == 0) {
         const uint32_t bytes = (uint32_t)p.n * 4u;
         mbar_expect_tx(bar, bytes * (1u + (p.gamma ? 1u : 0u)));
         tma_load_1d(xs, xsrc, bytes, bar);
         if (p.gamma) tma_load_1d(gs, p.gamma, bytes, bar);
     }
+    if (p.parts) {
+        // the wo / w2 product arrives split into nparts partial vectors (by head / by hidden slice):
+        // complete it in fixed order while the bulk copies are in flight
+        const float4 *pp = reinterpret_cast<const float4 *>(p.parts);
+        for (int i = tid; i < n4; i += NT) {
+            float4 a = __ldcg(pp + i);
+            for (int j = 1; j < p.nparts; ++j) {
+                const float4 d = __ldcg(pp + (size_t)j * n4 + i);
+                a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w;
+            }
+            reinterpret_cast<float4 *>(ps)[i] = a;
+        }
+    }
     __syncthreads();  // barrier init visible to all waiters
     mbar_wait(bar, 0);
-    if (p.gamma || p.x_out) {
+    if (p.gamma || p.x_out || p.parts) {
         float4 *xs4 = reinterpret_cast<float4 *>(xs);
         float ssq = 0.0f;
         for (int i = tid; i < n4; i += NT) {
-            const float4 v = xs4[i];
+            float4 v = xs4[i];
+            if (p.parts) {
+                const float4 d = reinterpret_cast<const float4 *>(ps)[i];
+                v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;   // accum(), :708-713
+                xs4[i] = v;
+            }
             if (p.x_out && blockIdx.x == 0) reinterpret_cast<float4 *>(p.x_out)[i] = v;
             ssq = fmaf(v.x, v.x, ssq); ssq = fmaf(v.y, v.y, ssq);
             ssq = fmaf(v.z, v.z, ssq); ssq = fmaf(v.w, v.w, ssq);
@@ -793,27 +821,42 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
         if (++p_stage == NSTAGE) { p_stage = 0; p_phase ^= 1; }
     };
     if (warp == NWARP) {
+        // ---- producer warp.  It runs on its own: issuing one stage costs ~0.5 us (8 bulk copies), so
+        // the other warps must not meet it at a barrier (measured r02: with the producer inside the
+        // prologue's barriers the activation vector was staged 5.3 us after the dependency wait, and
+        // the memory pipe sat idle behind a full ring).
         while (p_it < total && p_it < NSTAGE) produce_one();
         if (p_it >= total) pdl_launch_dependents();
         if (lane == 0) L2B_STAMP(p.trace, 1);
+        pdl_wait();
+        if (!p.ctl[CTL_DONE]) {
+            while (p_it < total) {
+                produce_one();
+                if (p_it == total) pdl_launch_dependents();   // last stage in flight
+            }
+            if (lane == 0) L2B_STAMP(p.trace, 6);
+            return;
+        }
     }
 
     // the rmsnorm gain is immutable: fetch this thread's slice before waiting on the previous
     // kernel (on big models it has been evicted from L2 by the weight stream, and after the wait
     // its DRAM round trip would queue behind this CTA's own ring traffic)
-    constexpr int MAXV = 4;                               // n <= 4 * 320 * 4 = 5120 floats when fused
+    constexpr int MAXV = 5;                               // n <= 5 * 288 * 4 = 5760 floats when fused
+    constexpr int PRO_THREADS = TMA_THREADS - 32;         // consumers + epilogue warp
+    const int ptid = tid < NT ? tid : tid - 32;           // index among the prologue's threads
     float4 gv[MAXV];
-    if (p.gamma) {
+    if (p.gamma && warp != NWARP) {
         const float4 *g4 = reinterpret_cast<const float4 *>(p.gamma);
 #pragma unroll
         for (int k = 0; k < MAXV; ++k) {
-            const int i = tid + k * TMA_THREADS;
+            const int i = ptid + k * PRO_THREADS;
             gv[k] = (i < n4) ? __ldg(g4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
 
     // ---- everything below reads what earlier kernels of this step wrote
-    pdl_wait();
+    if (warp != NWARP) pdl_wait();
     if (p.ctl[CTL_DONE]) {
         // generation already ended: drain the bulk copies already aimed at our shared memory
         if (tid == 0)
@@ -825,10 +868,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
     if (p.bump_epoch && blockIdx.x == 0 && tid == 0) const_cast<int *>(p.ctl)[CTL_EPOCH] += 1;
     if (tid == 0) L2B_STAMP(p.trace, 2);
 
-    // stage the activation vector (all threads take part in the barriers of this phase)
+    // stage the activation vector (consumer warps + epilogue warp; barrier 1 is theirs)
     {
-        if (p.ll_in) tp_reduce_into_x(p);                 // tensor parallel: x += sum of all ranks' partial rows
         const float *xsrc = p.emb ? p.emb + (size_t)p.ctl[CTL_TOKEN] * p.n : p.x_in;
+        if (p.ll_in) tp_reduce_into_x(p, 1, PRO_THREADS);  // tensor parallel: x += sum of all ranks' partial rows
         if (tid == 0) {
             const uint32_t bytes = (uint32_t)p.n * 4u;
             mbar_expect_tx(&xbar, bytes);
@@ -847,7 +890,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
             float ssq = 0.0f;
 #pragma unroll
             for (int k = 0; k < MAXV; ++k) {
-                const int i = tid + k * TMA_THREADS;
+                const int i = ptid + k * PRO_THREADS;
                 if (i < n4) {
                     const float4 v = xs4w[i];
                     if (p.x_out && blockIdx.x == 0) reinterpret_cast<float4 *>(p.x_out)[i] = v;
@@ -857,16 +900,16 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
             }
             if (p.gamma) {
                 ssq = warp_sum(ssq);
-                if (lane == 0) scratch[warp] = ssq;
-                __syncthreads();
-                float ss = (lane < NWARP + 2) ? scratch[lane] : 0.0f;
+                if (lane == 0) scratch[ptid >> 5] = ssq;
+                named_bar_sync(1, PRO_THREADS);
+                float ss = (lane < PRO_THREADS / 32) ? scratch[lane] : 0.0f;
                 ss = warp_sum(ss);
                 ss /= (float)p.n;            // :452
                 ss += 1e-5f;                 // :453
                 const float sc = 1.0f / sqrtf(ss);  // :454
 #pragma unroll
                 for (int k = 0; k < MAXV; ++k) {
-                    const int i = tid + k * TMA_THREADS;
+                    const int i = ptid + k * PRO_THREADS;
                     if (i < n4) {
                         float4 v = xs4w[i];
                         v.x = __fmul_rn(__fmul_rn(v.x, sc), gv[k].x);   // (x*s)*w, :462
@@ -878,19 +921,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
                 }
             }
         }
-        __syncthreads();
+        named_bar_sync(1, PRO_THREADS);
     }
     if (tid == 0) L2B_STAMP(p.trace, 3);
-
-    if (warp == NWARP) {
-        // ---- producer warp: keep the ring full
-        while (p_it < total) {
-            produce_one();
-            if (p_it == total) pdl_launch_dependents();   // last stage in flight
-        }
-        if (lane == 0) L2B_STAMP(p.trace, 6);
-        return;
-    }
 
     if (warp == NWARP + 1) {
         // ---- epilogue warp: lanes 0..3 own the four row pairs of each tile
@@ -1333,6 +1366,263 @@ __global__ void __launch_bounds__(NT) attention_flash_kernel(const AttnParams p)
         float a2 = 0.0f;
         for (int j = 0; j < active; ++j) a2 = fmaf(expf(ml[j * 2] - MM), pb[(size_t)j * hs + tid], a2);
         p.xb[(size_t)h * hs + tid] = a2 / Lsum;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Small models (stories15M / 110M): a decode step there is a chain of ~3 us kernels that move
+// <= 2 MB each, so the step time is the NUMBER of kernels.  Two fusions take a layer from five
+// kernels to three (qkv_rope -> attn_wo -> ffn):
+//
+// attn_wo_kernel: attention of one head (:361-389) + that head's column slice of wo (:392) in one
+//   thread-block CLUSTER of R CTAs.  CTA s of the cluster runs flash-decoding over timeline split s;
+//   the R partial (max, sum, unnormalised out) triples are merged through DISTRIBUTED SHARED MEMORY
+//   (every CTA reads its peers' triples after a cluster barrier, in fixed split order), then CTA s
+//   multiplies the merged head output with rows [s*dim/R, (s+1)*dim/R) of wo[:, h*hs:(h+1)*hs] and
+//   writes parts[h][row].  The consumer's prologue completes the product: x += sum_h parts[h]
+//   (fixed head order), which is the wo GEMV's own summation split at head boundaries.
+// ffn_fused_kernel (dim <= 512): CTA j owns 32 hidden units: rmsnorm prologue, the 32 (w1, w3) row
+//   pairs + SiLU*mul (:398-416), then the matching 32-column slice of w2 (:419) -> parts[j][dim].
+// ---------------------------------------------------------------------------------------
+struct AttnWoParams {
+    AttnParams a;
+    const float *wo;        // this layer's (dim, q_dim) row-major
+    float *parts;           // (n_heads, dim)
+    int dim, q_dim;
+};
+
+template <int NF>   // float4 per lane per row: head_size = 4 * NF * LPR
+__global__ void __launch_bounds__(NT) attn_wo_kernel(const AttnWoParams q) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const AttnParams &p = q.a;
+    const int h = blockIdx.x, s = blockIdx.y, R = gridDim.y;     // cluster = the R CTAs of one head
+    const int hs = p.head_size, hs4 = hs >> 2;
+    const int LPR = hs4 / NF, RPW = 32 / LPR, NG = NWARP * RPW;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lr = lane % LPR, rw = lane / LPR;
+    const int grp = warp * RPW + rw;
+    float *accp = reinterpret_cast<float *>(smem_raw);        // [NG][hs]
+    float *mlp = accp + (size_t)NG * hs;                      // [NG][2]
+    float *wgt = mlp + 2 * NG;                                // [NG]
+    float *tri = wgt + NG;                                    // [hs + 4]: this CTA's unnormalised out, M, L
+    float *xbs = tri + hs + 4;                                // [hs]: merged head output
+    __shared__ float sh_L;
+
+    // rows of the wo slice this CTA produces; the first pass of weights is immutable: fetch it now
+    const int rows_per = (q.dim + R - 1) / R;
+    const int r0 = s * rows_per, r1 = min(q.dim, r0 + rows_per);
+    const float4 *wo4 = reinterpret_cast<const float4 *>(q.wo) + (size_t)h * hs4;
+    const int q4 = q.q_dim >> 2;
+    float4 wpre[NF];
+    {
+        const int row = r0 + warp * RPW + rw;
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+            wpre[f] = (row < r1) ? ldg_stream(wo4 + (size_t)row * q4 + lr + f * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    pdl_launch_dependents();
+    pdl_wait();
+    if (p.ctl[CTL_DONE]) return;                               // uniform over the whole grid
+
+    const int T = p.ctl[CTL_POS] + 1;
+    const int chunk = (T + R - 1) / R;
+    const int t0 = s * chunk, t1 = min(T, t0 + chunk);         // may be empty (t0 >= T)
+    const size_t hoff = (size_t)(h / p.kv_mul) * hs;           // :369, :382
+    const float4 *qv4 = reinterpret_cast<const float4 *>(p.q + (size_t)h * hs);
+    const float *kb = p.kcache + hoff, *vb = p.vcache + hoff;
+    const float root_hs = sqrtf((float)hs);
+
+    float4 qf[NF], acc[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        qf[f] = __ldcg(qv4 + lr + f * LPR);
+        acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float m = -INFINITY, l = 0.0f;
+    auto update = [&](const float4 (&kv)[NF], const float4 (&vv)[NF], bool valid) {
+        float sc = 0.0f;
+#pragma unroll
+        for (int f = 0; f < NF; ++f) sc = dot4(kv[f], qf[f], sc);
+        for (int o = LPR >> 1; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+        if (!valid) return;
+        sc = sc / root_hs;                                    // :372
+        const float mn = fmaxf(m, sc);
+        const float scale = expf(m - mn);
+        const float pw = expf(sc - mn);
+        l = fmaf(l, scale, pw);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            acc[f].x = fmaf(acc[f].x, scale, pw * vv[f].x);
+            acc[f].y = fmaf(acc[f].y, scale, pw * vv[f].y);
+            acc[f].z = fmaf(acc[f].z, scale, pw * vv[f].z);
+            acc[f].w = fmaf(acc[f].w, scale, pw * vv[f].w);
+        }
+        m = mn;
+    };
+    for (int tbw = t0 + warp * RPW; tbw < t1; tbw += 2 * NG) {   // warp-uniform bound (full-mask shuffles inside)
+        const int ta = tbw + rw, tc = ta + NG;
+        const bool va = ta < t1, vc = tc < t1;
+        float4 ka[NF], vA[NF], kc[NF], vC[NF];
+        const float4 *ka4 = reinterpret_cast<const float4 *>(kb + (size_t)(va ? ta : t0) * p.kv_dim);
+        const float4 *va4 = reinterpret_cast<const float4 *>(vb + (size_t)(va ? ta : t0) * p.kv_dim);
+        const float4 *kc4 = reinterpret_cast<const float4 *>(kb + (size_t)(vc ? tc : t0) * p.kv_dim);
+        const float4 *vc4 = reinterpret_cast<const float4 *>(vb + (size_t)(vc ? tc : t0) * p.kv_dim);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            ka[f] = __ldcg(ka4 + lr + f * LPR);
+            vA[f] = __ldcg(va4 + lr + f * LPR);
+            kc[f] = __ldcg(kc4 + lr + f * LPR);
+            vC[f] = __ldcg(vc4 + lr + f * LPR);
+        }
+        update(ka, vA, va);
+        update(kc, vC, vc);
+    }
+    // ---- merge the NG row groups of this CTA (fixed order)
+#pragma unroll
+    for (int f = 0; f < NF; ++f)
+        reinterpret_cast<float4 *>(accp + (size_t)grp * hs)[lr + f * LPR] = acc[f];
+    if (lr == 0) { mlp[2 * grp] = m; mlp[2 * grp + 1] = l; }
+    __syncthreads();
+    if (warp == 0) {
+        float M = -INFINITY;
+        for (int g = lane; g < NG; g += 32) M = fmaxf(M, mlp[2 * g]);
+        M = warp_max(M);
+        float L = 0.0f;
+        for (int g = lane; g < NG; g += 32) {
+            const float w = (mlp[2 * g] == -INFINITY) ? 0.0f : expf(mlp[2 * g] - M);   // empty groups (and empty splits: M = -inf)
+            wgt[g] = w;
+            L = fmaf(w, mlp[2 * g + 1], L);
+        }
+        L = warp_sum(L);
+        if (lane == 0) { sh_L = L; tri[hs] = M; tri[hs + 1] = L; }
+    }
+    __syncthreads();
+    if (tid < hs) {
+        float o = 0.0f;
+        for (int g = 0; g < NG; ++g) o = fmaf(wgt[g], accp[(size_t)g * hs + tid], o);
+        tri[tid] = o;
+    }
+    // ---- merge the R timeline splits of the head through distributed shared memory
+    cluster.sync();
+    {
+        float MM = -INFINITY;
+        for (int j = 0; j < R; ++j) MM = fmaxf(MM, cluster.map_shared_rank(tri, j)[hs]);
+        float Lsum = 0.0f, a2 = 0.0f;
+        for (int j = 0; j < R; ++j) {                          // fixed split order => deterministic
+            const float *tj = cluster.map_shared_rank(tri, j);
+            const float Mj = tj[hs];
+            const float w = (Mj == -INFINITY) ? 0.0f : expf(Mj - MM);
+            Lsum = fmaf(w, tj[hs + 1], Lsum);
+            if (tid < hs) a2 = fmaf(w, tj[tid], a2);
+        }
+        if (tid < hs) xbs[tid] = a2 / Lsum;                    // softmax normalisation, :703-705
+    }
+    cluster.sync();                                            // peers are done reading this CTA's triple
+
+    // ---- this CTA's rows of wo[:, h*hs:(h+1)*hs] . xb_h
+    const float4 *xb4 = reinterpret_cast<const float4 *>(xbs);
+    bool first = true;
+    for (int rb = r0 + warp * RPW; rb < r1; rb += NG) {        // warp-uniform bound
+        const int row = rb + rw;
+        const bool valid = row < r1;
+        float a = 0.0f;
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            const float4 w = first ? wpre[f]
+                                   : (valid ? ldg_stream(wo4 + (size_t)row * q4 + lr + f * LPR) : make_float4(0.f, 0.f, 0.f, 0.f));
+            a = dot4(w, xb4[lr + f * LPR], a);
+        }
+        first = false;
+        for (int o = LPR >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (valid && lr == 0) q.parts[(size_t)h * q.dim + row] = a;
+    }
+}
+
+constexpr int FFN_HSZ = 32;       // hidden units per CTA = NT / 8 (one (w1, w3) row pair per 8-lane group)
+constexpr int FFN_MAXU = 16;      // float4 columns per lane: dim <= 8 * 16 * 4 = 512
+struct FfnParams {
+    GemvParams g;           // prologue: x_in, parts/nparts, gamma, x_out, n = dim, ctl
+    const float *w1, *w3;   // this layer's (hidden, dim)
+    const float *w2;        // this layer's (dim, hidden)
+    float *out_parts;       // (hidden / 32, dim)
+    int hidden;
+};
+
+__global__ void __launch_bounds__(NT) ffn_fused_kernel(const FfnParams q) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const GemvParams &p = q.g;
+    float *xs = reinterpret_cast<float *>(smem_raw);   // dim floats
+    float *aux = xs + p.n;                              // gamma (dim) then the parts sum (dim)
+    __shared__ uint64_t bar;
+    __shared__ float scratch[NWARP + 1];
+    __shared__ __align__(16) float hb_s[FFN_HSZ];
+    const int tid = threadIdx.x, grp = tid >> 3, sub = tid & 7;
+    const int n4 = p.n >> 2;
+    const int j = blockIdx.x;                           // hidden slice [j*32, j*32+32)
+    const int hrow = j * FFN_HSZ + grp;
+
+    // ---- immutable weights first: this lane's share of one (w1, w3) row pair, and of the first w2 pass
+    float4 wa[FFN_MAXU], wb[FFN_MAXU];
+    {
+        const float4 *r1 = reinterpret_cast<const float4 *>(q.w1 + (size_t)hrow * p.n);
+        const float4 *r3 = reinterpret_cast<const float4 *>(q.w3 + (size_t)hrow * p.n);
+#pragma unroll
+        for (int u = 0; u < FFN_MAXU; ++u) {
+            const int c = u * 8 + sub;
+            wa[u] = (c < n4) ? ldg_stream(r1 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            wb[u] = (c < n4) ? ldg_stream(r3 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    pdl_launch_dependents();
+    pdl_wait();
+    if (p.ctl[CTL_DONE]) return;
+    gemv_stage_input(p, xs, aux, &bar, scratch);
+
+    // ---- hb slice = silu(w1 . xs) * (w3 . xs)
+    const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
+    float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+    for (int u = 0; u < FFN_MAXU; ++u) {
+        const int c = u * 8 + sub;
+        if (c < n4) {
+            const float4 xv = xs4[c];
+            a0 = dot4(wa[u], xv, a0);
+            a1 = dot4(wb[u], xv, a1);
+        }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (sub == 0) {
+        const float sg = __fmul_rn(a0, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-a0))));   // :412
+        hb_s[grp] = __fmul_rn(sg, a1);                                                // :416
+    }
+    __syncthreads();
+
+    // ---- partial of w2: out[i] = sum_{k in slice} w2[i][j*32 + k] * hb[k]; 2 lanes per row, 4 float4 each
+    const float4 *hb4 = reinterpret_cast<const float4 *>(hb_s);
+    const int half = tid & 1;
+    const float4 *w24 = reinterpret_cast<const float4 *>(q.w2) + (size_t)j * (FFN_HSZ / 4) + half * 4;
+    const int h4 = q.hidden >> 2;
+    for (int ib = 0; ib < p.n; ib += NT / 2) {           // warp-uniform bound
+        const int i = ib + (tid >> 1);
+        const bool valid = i < p.n;
+        float a = 0.0f;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            const float4 w = valid ? ldg_stream(w24 + (size_t)i * h4 + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+            a = dot4(w, hb4[half * 4 + f], a);
+        }
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        if (valid && half == 0) q.out_parts[(size_t)j * p.n + i] = a;
     }
 }
 

@@ -102,6 +102,11 @@ struct l2b_ctx {
     float *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *wcls = nullptr;
     // device run state (RunState, :119-135)
     float *X = nullptr;                      // residual stream x; wo / w2 add into it (:395, :422)
+    float *Xalt = nullptr;                   // second copy: kernels that fold partial vectors in write the new x here (ping-pong)
+    float *final_X = nullptr;                // which of the two holds x after a step
+    float *attn_parts = nullptr, *ffn_parts = nullptr;   // small-model fusion: (n_heads, dim) and (hidden/32, dim) partial vectors
+    bool fuse_attn = false, fuse_ffn = false;
+    int attn_R = 1;                          // CTAs per head cluster of attn_wo_kernel
     float *delta = nullptr;                  // L2B_TP=nccl baseline only: partial rows before the NCCL all-reduce
     float *q = nullptr, *xb = nullptr, *hb = nullptr, *logits = nullptr, *logits_loc = nullptr;
     float *kcache = nullptr, *vcache = nullptr;     // (L, seq_len, kv_loc)
@@ -434,7 +439,7 @@ int launch_gemv(l2b_ctx *ctx, int epi, const GemvParams &p, cudaStream_t st, con
         int prc = prof_mark(ctx, name, layer, (uint64_t)p.total_rows * p.n * 4ull, st);
         if (prc) return prc;
     }
-    const size_t xbytes = (size_t)p.n * 4 * (1 + (p.gamma ? 1 : 0));
+    const size_t xbytes = (size_t)p.n * 4 * (1 + (p.gamma ? 1 : 0) + (p.parts ? 1 : 0));
     // bandwidth-bound shapes take the TMA-ring kernel (or the register-fed 8-row kernel when
     // L2B_GEMV_BIG=ldg), latency-bound ones the fine-grained kernel
     bool big = ctx->gemv8_min_bytes >= 0 && p.n >= ctx->big_min_n &&
@@ -448,7 +453,8 @@ int launch_gemv(l2b_ctx *ctx, int epi, const GemvParams &p, cudaStream_t st, con
     const size_t xonly = (size_t)p.n * 4;
     int nstage = ctx->tma_stages > 0 ? ctx->tma_stages : (int)(((size_t)kMaxSmemOptin - xonly) / stage_bytes);
     if (nstage > TMA_MAX_STAGES) nstage = TMA_MAX_STAGES;
-    const bool fused_ok = !p.gamma || p.n <= 4 * TMA_THREADS * 4;   // register slices of the rmsnorm gain
+    const bool fused_ok = !p.gamma || p.n <= 5 * (TMA_THREADS - 32) * 4;   // register slices of the rmsnorm gain (MAXV x prologue threads)
+    if (p.parts && big) return fail(ctx, L2B_ERR_UNSUPPORTED, "partial-vector prologue is only in the latency kernel");
     bool tma = big && ctx->big_kernel_tma && nstage >= 2 && fused_ok && p.head_size <= 256 &&
                (size_t)nstage * stage_bytes + xonly <= (size_t)kMaxSmemOptin;
     if (ctx->force_kernel == 2) tma = false;
@@ -522,6 +528,91 @@ attn_fn pick_attention(int head_size, bool flash, size_t *smem) {
     const int ng = NWARP * (32 / lpr);
     *smem = ((size_t)ng * head_size + 3 * (size_t)ng) * sizeof(float);
     return f2;
+}
+
+typedef void (*attn_wo_fn)(const AttnWoParams);
+attn_wo_fn pick_attn_wo(int head_size, size_t *smem) {
+    const int hs4 = head_size / 4;
+    const int lpr = (hs4 % 8 == 0) ? 8 : (hs4 % 4 == 0) ? 4 : (hs4 % 2 == 0) ? 2 : 1;
+    const int nf = hs4 / lpr;
+    const int ng = NWARP * (32 / lpr);
+    *smem = ((size_t)ng * head_size + 3 * (size_t)ng + 2 * (size_t)head_size + 4) * sizeof(float);
+    switch (nf) {
+    case 1: return attn_wo_kernel<1>;
+    case 2: return attn_wo_kernel<2>;
+    case 3: return attn_wo_kernel<3>;
+    case 4: return attn_wo_kernel<4>;
+    case 5: return attn_wo_kernel<5>;
+    case 6: return attn_wo_kernel<6>;
+    case 8: return attn_wo_kernel<8>;
+    default: return nullptr;
+    }
+}
+
+// attention + wo of one layer in one cluster launch (small models): partial vectors -> ctx->attn_parts
+int launch_attn_wo(l2b_ctx *ctx, int layer, cudaStream_t st) {
+    if (ctx->profiling) {
+        const int hpos = ctx->n_appended > 0 ? ctx->n_appended - 1 : 0;
+        int prc = prof_mark(ctx, "attn_wo", layer, 2ull * (uint64_t)(hpos + 1) * ctx->kv_loc * 4ull + (uint64_t)ctx->dim * ctx->q_loc * 4ull, st);
+        if (prc) return prc;
+    }
+    AttnWoParams q{};
+    AttnParams &a = q.a;
+    a.ctl = ctx->ctl;
+    a.q = ctx->q;
+    const size_t loff = (size_t)layer * ctx->cfg.seq_len * ctx->kv_loc;   // :354
+    a.kcache = ctx->kcache + loff;
+    a.vcache = ctx->vcache + loff;
+    a.head_size = ctx->head_size;
+    a.kv_dim = ctx->kv_loc;
+    a.kv_mul = ctx->kv_mul;
+    a.trace = nullptr;
+    q.wo = ctx->wo + (size_t)layer * ctx->dim * ctx->q_loc;
+    q.parts = ctx->attn_parts;
+    q.dim = ctx->dim;
+    q.q_dim = ctx->q_loc;
+    size_t smem = 0;
+    attn_wo_fn fn = pick_attn_wo(ctx->head_size, &smem);
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(ctx->heads_loc, ctx->attn_R);
+    lc.blockDim = dim3(NT);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = ctx->attn_R; at[0].val.clusterDim.z = 1;
+    at[1] = pdl_attr();
+    lc.attrs = at;
+    lc.numAttrs = ctx->use_pdl ? 2 : 1;
+    L2B_CUDA(ctx, cudaLaunchKernelEx(&lc, fn, q));
+    ++ctx->last_launches;
+    return L2B_OK;
+}
+
+// rmsnorm + w1/w3 + SiLU*mul + w2 of one layer in one launch (dim <= 512): partial vectors -> ctx->ffn_parts
+int launch_ffn_fused(l2b_ctx *ctx, int layer, const GemvParams &g, cudaStream_t st) {
+    const uint64_t bytes = 3ull * ctx->hid_loc * ctx->dim * 4ull;
+    int prc = prof_mark(ctx, "ffn", layer, bytes, st);
+    if (prc) return prc;
+    FfnParams q{};
+    q.g = g;
+    q.g.spin_ns = ctx->spin_ns;
+    q.w1 = ctx->w1 + (size_t)layer * ctx->hid_loc * ctx->dim;
+    q.w3 = ctx->w3 + (size_t)layer * ctx->hid_loc * ctx->dim;
+    q.w2 = ctx->w2 + (size_t)layer * ctx->dim * ctx->hid_loc;
+    q.out_parts = ctx->ffn_parts;
+    q.hidden = ctx->hid_loc;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(ctx->hid_loc / FFN_HSZ);
+    lc.blockDim = dim3(NT);
+    lc.dynamicSmemBytes = (size_t)ctx->dim * 4 * 3;
+    lc.stream = st;
+    cudaLaunchAttribute at[1] = {pdl_attr()};
+    lc.attrs = at;
+    lc.numAttrs = ctx->use_pdl ? 1 : 0;
+    L2B_CUDA(ctx, cudaLaunchKernelEx(&lc, ffn_fused_kernel, q));
+    ++ctx->last_launches;
+    return L2B_OK;
 }
 
 int launch_attention(l2b_ctx *ctx, int layer, cudaStream_t st) {
@@ -623,11 +714,11 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, StepMode mode) {
         for (int r = 0; r < ctx->world; ++r) g.ll_out[r] = ll_red_at(ctx->peer_arena[r], ctx, slot, ctx->rank);
     };
     // wo / w2: row-parallel GEMV whose result is added to the residual stream (:392-395, :419-422)
-    auto residual_gemv = [&](GemvParams &g, int slot, const char *name, int l) -> int {
+    auto residual_gemv = [&](GemvParams &g, float *x, int slot, const char *name, int l) -> int {
         g.total_rows = dim; g.rows0 = dim;
         int rc;
         if (!tp) {
-            g.out0 = ctx->X;
+            g.out0 = x;
             rc = launch_gemv(ctx, EPI_RESID, g, st, name, l);
         } else if (p2p) {
             produce_slot(g, slot);
@@ -637,21 +728,35 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, StepMode mode) {
             rc = launch_gemv(ctx, EPI_STORE, g, st, name, l);
             if (rc) return rc;
             L2B_NCCL(ctx, g_nccl.AllReduce(ctx->delta, ctx->delta, dim, ncclFloat, ncclSum, ctx->comm, st));
-            resid_add_kernel<<<(dim + NT - 1) / NT, NT, 0, st>>>(ctx->X, ctx->delta, dim, ctx->ctl);
+            resid_add_kernel<<<(dim + NT - 1) / NT, NT, 0, st>>>(x, ctx->delta, dim, ctx->ctl);
             L2B_CUDA(ctx, cudaGetLastError());
             ++ctx->last_launches;
         }
         return rc;
+    };
+    // small-model fusion (world == 1): attention+wo and the whole FFN leave their result as partial
+    // vectors that the NEXT kernel's prologue sums into x; such a kernel reads x from one buffer and
+    // CTA 0 writes the new x to the other (ping-pong), everything else updates x in place
+    float *Xc = ctx->X, *Xo = ctx->Xalt;
+    const float *pend = nullptr;             // partial vectors still to be folded into x
+    int npend = 0;
+    auto fold_pending = [&](GemvParams &g) {
+        g.x_in = Xc;
+        if (pend) {
+            g.parts = pend; g.nparts = npend; g.x_out = Xo;
+            float *t = Xc; Xc = Xo; Xo = t;
+            pend = nullptr; npend = 0;
+        }
     };
     for (int l = 0; l < c.n_layers; ++l) {
         // ---- rmsnorm + q,k,v + RoPE + KV append (:305-358)
         GemvParams p{};
         p.ctl = ctx->ctl;
         p.n = dim;
-        p.x_in = ctx->X;
+        fold_pending(p);
         if (l == 0) {
             p.emb = ctx->emb;                 // :295-296
-            p.x_out = ctx->X;
+            p.x_out = Xc;
             p.bump_epoch = 1;
         } else if (p2p) {
             consume_slot(p, 2 * (l - 1) + 1); // pending :422 of the previous layer
@@ -671,26 +776,40 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, StepMode mode) {
         int rc = launch_gemv(ctx, EPI_QKV, p, st, "qkv_rope", l);
         if (rc) return rc;
 
-        // ---- attention (:361-389)
-        rc = launch_attention(ctx, l, st);
-        if (rc) return rc;
-
-        // ---- wo + residual (:392-395)
-        GemvParams o{};
-        o.ctl = ctx->ctl;
-        o.n = ctx->q_loc;
-        o.x_in = ctx->xb;
-        o.w0 = ctx->wo + (size_t)l * dim * ctx->q_loc;
-        rc = residual_gemv(o, 2 * l, "wo", l);
-        if (rc) return rc;
+        if (ctx->fuse_attn) {
+            // ---- attention + wo in one cluster launch (:361-392); the add of :395 happens in the next prologue
+            rc = launch_attn_wo(ctx, l, st);
+            if (rc) return rc;
+            pend = ctx->attn_parts; npend = ctx->heads_loc;
+        } else {
+            // ---- attention (:361-389)
+            rc = launch_attention(ctx, l, st);
+            if (rc) return rc;
+            // ---- wo + residual (:392-395)
+            GemvParams o{};
+            o.ctl = ctx->ctl;
+            o.n = ctx->q_loc;
+            o.x_in = ctx->xb;
+            o.w0 = ctx->wo + (size_t)l * dim * ctx->q_loc;
+            rc = residual_gemv(o, Xc, 2 * l, "wo", l);
+            if (rc) return rc;
+        }
 
         // ---- rmsnorm + w1,w3 + SiLU*mul (:398-416)
         GemvParams f{};
         f.ctl = ctx->ctl;
         f.n = dim;
-        f.x_in = ctx->X;
+        fold_pending(f);
         if (p2p) consume_slot(f, 2 * l);
         f.gamma = ctx->rms_ffn + (size_t)l * dim;
+        if (ctx->fuse_ffn && l + 1 < c.n_layers) {
+            // ---- ... + w2 in the same launch (:419); the last layer stays unfused so that the
+            // classifier's many CTAs stage a finished x instead of each summing the partial vectors
+            rc = launch_ffn_fused(ctx, l, f, st);
+            if (rc) return rc;
+            pend = ctx->ffn_parts; npend = ctx->hid_loc / FFN_HSZ;
+            continue;
+        }
         f.w0 = ctx->w1 + (size_t)l * ctx->hid_loc * dim;
         f.w1 = ctx->w3 + (size_t)l * ctx->hid_loc * dim;
         f.rows0 = ctx->hid_loc;
@@ -705,14 +824,15 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, StepMode mode) {
         d.n = ctx->hid_loc;
         d.x_in = ctx->hb;
         d.w0 = ctx->w2 + (size_t)l * dim * ctx->hid_loc;
-        rc = residual_gemv(d, 2 * l + 1, "w2", l);
+        rc = residual_gemv(d, Xc, 2 * l + 1, "w2", l);
         if (rc) return rc;
     }
     // ---- final rmsnorm + classifier (:426-429)
     GemvParams k{};
     k.ctl = ctx->ctl;
     k.n = dim;
-    k.x_in = ctx->X;
+    fold_pending(k);
+    ctx->final_X = Xc;
     if (p2p) consume_slot(k, 2 * (c.n_layers - 1) + 1);
     k.gamma = ctx->rms_final;
     k.w0 = ctx->wcls;
@@ -861,6 +981,8 @@ int preload_kernels(l2b_ctx *ctx) {
     }
     size_t smem = 0;
     L2B_CUDA(ctx, cudaFuncGetAttributes(&fa, (const void *)pick_attention(ctx->head_size, true, &smem)));
+    if (pick_attn_wo(ctx->head_size, &smem)) L2B_CUDA(ctx, cudaFuncGetAttributes(&fa, (const void *)pick_attn_wo(ctx->head_size, &smem)));
+    L2B_CUDA(ctx, cudaFuncGetAttributes(&fa, (const void *)ffn_fused_kernel));
     const void *others[] = {(const void *)attention_kernel, (const void *)advance_kernel, (const void *)gather_logits_kernel,
                             (const void *)resid_add_kernel, (const void *)sample_prep_kernel, (const void *)synth_fill_kernel};
     for (const void *f : others) L2B_CUDA(ctx, cudaFuncGetAttributes(&fa, f));
@@ -938,6 +1060,20 @@ int create_rank(l2b_ctx *ctx, const l2b_config *cfg, const Source &src, const fl
 
     // ---- run state
     L2B_TRY(dev_alloc(ctx, &ctx->X, dim));
+    L2B_TRY(dev_alloc(ctx, &ctx->Xalt, dim));
+    {
+        // small-model fusion (measured on B200, profiles/r02_small_models.md): a step of stories15M is 31
+        // kernels of ~3 us; attention+wo as one cluster kernel and the FFN as one kernel make it 20
+        const char *ef = getenv("L2B_FUSE");
+        const int want = ef ? atoi(ef) : 3;                       // bit 0: attention+wo, bit 1: FFN
+        size_t smem_aw = 0;
+        ctx->fuse_attn = (want & 1) && world == 1 && dim < 1024 && pick_attn_wo((int)hs, &smem_aw) != nullptr;
+        ctx->fuse_ffn = (want & 2) && world == 1 && dim <= 8 * FFN_MAXU * 4 && hid % FFN_HSZ == 0;
+        const char *er = getenv("L2B_ATTN_R");
+        ctx->attn_R = er && atoi(er) >= 1 && atoi(er) <= 8 ? atoi(er) : 4;
+        if (ctx->fuse_attn) L2B_TRY(dev_alloc(ctx, &ctx->attn_parts, (size_t)cfg->n_heads * dim));
+        if (ctx->fuse_ffn) L2B_TRY(dev_alloc(ctx, &ctx->ffn_parts, (size_t)(hid / FFN_HSZ) * dim));
+    }
     L2B_TRY(dev_alloc(ctx, &ctx->delta, dim));
     L2B_TRY(dev_alloc(ctx, &ctx->q, (size_t)ctx->q_loc));
     L2B_TRY(dev_alloc(ctx, &ctx->xb, (size_t)ctx->q_loc));
@@ -1509,7 +1645,7 @@ int32_t l2b_read_state(l2b_ctx *ctx, int32_t which, float *dst, uint64_t n, uint
     uint64_t cnt = 0;
     const uint64_t L = ctx->cfg.n_layers, S = ctx->cfg.seq_len;
     switch (which) {
-    case 0: src = ctx->X; cnt = ctx->dim; break;
+    case 0: src = ctx->final_X ? ctx->final_X : ctx->X; cnt = ctx->dim; break;
     case 1: src = ctx->xb; cnt = ctx->q_loc; break;
     case 2: src = ctx->hb; cnt = ctx->hid_loc; break;
     case 3: src = ctx->q; cnt = ctx->q_loc; break;
