@@ -253,7 +253,8 @@ def load_host_twin():
 
     class GenOptions(C.Structure):
         _fields_ = [("temperature", C.c_float), ("top_p", C.c_float), ("n_steps", C.c_int32),
-                    ("stop_on_bos", C.c_int32), ("use_device_argmax", C.c_int32)]
+                    ("stop_on_bos", C.c_int32), ("use_device_argmax", C.c_int32), ("use_prefill", C.c_int32),
+                    ("use_device_sampler", C.c_int32)]
 
     class GenResult(C.Structure):
         _fields_ = [("n_forward", C.c_int32), ("n_tokens", C.c_int32), ("secs_total", C.c_double),
@@ -323,7 +324,7 @@ def run_workload(workload, args, rank, world, dist, sync, flush, clock_index):
         return t.last_timing()
 
     host_lib, GenOptions, GenResult = load_host_twin()
-    opt = GenOptions(0.0, 0.9, positions, 0, 0)
+    opt = GenOptions(0.0, 0.9, positions, 0, 0, 0, 0)
     res = GenResult()
     prompt = None if forced is None else forced.ctypes.data_as(C.POINTER(C.c_int32))
     n_prompt = 0 if forced is None else positions

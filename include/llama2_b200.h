@@ -163,6 +163,17 @@ int32_t l2b_generate_argmax(l2b_ctx *ctx, int32_t token, int32_t pos, int32_t n_
                             const int32_t *forced, int32_t stop_on_bos, int32_t *out_next,
                             int32_t *n_done);
 
+/* Prompt prefill.  The reference feeds prompt tokens through transformer() one at
+ * a time and discards their logits (src/main.zig:996-1000).  This runs positions pos0 ..
+ * pos0+n_tokens-1 with tokens[i] at position pos0+i back to back on the device: no host round trip
+ * per position, and the classifier is skipped for every position whose logits nobody reads.
+ * host_logits == NULL: no logits at all (the KV cache is all the caller wants); otherwise the
+ * logits of the LAST position are returned, exactly as l2b_forward would.  Per position the
+ * arithmetic is the decode step's own, so KV cache and logits equal n_tokens calls of
+ * l2b_forward bit for bit.                                                                 */
+int32_t l2b_prefill(l2b_ctx *ctx, const int32_t *tokens, int32_t n_tokens, int32_t pos0,
+                    float *host_logits);
+
 /* ---- introspection ------------------------------------------------------------------- */
 
 const char *l2b_last_error(const l2b_ctx *ctx);     /* never NULL                           */

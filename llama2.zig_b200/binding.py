@@ -87,6 +87,7 @@ def load_library():
     lib.l2b_forward_argmax.argtypes = [vp, C.c_int32, C.c_int32, IP]
     lib.l2b_forward_pinned.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(FP)]
     lib.l2b_generate_argmax.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, IP, C.c_int32, IP, IP]
+    lib.l2b_prefill.argtypes = [vp, IP, C.c_int32, C.c_int32, FP]
     lib.l2b_logits_buffer.argtypes = [vp]
     lib.l2b_logits_buffer.restype = FP
     lib.l2b_forward_sample.argtypes = [vp, C.c_int32, C.c_int32, C.c_float, C.c_float, FP,
@@ -249,6 +250,15 @@ class Transformer:
         nxt = C.c_int32()
         _check(self.lib.l2b_forward_argmax(self.h, int(token), int(pos), C.byref(nxt)), self.h)
         return nxt.value
+
+    def prefill(self, tokens, pos0=0, want_logits=True):
+        """tokens[i] at position pos0+i, all on the device (src/main.zig:996-1000 without the host loop);
+        returns the logits of the last position, or None with want_logits=False."""
+        toks = np.ascontiguousarray(tokens, dtype=np.int32)
+        out = self._logits if want_logits else None
+        _check(self.lib.l2b_prefill(self.h, toks.ctypes.data_as(IP), toks.size, int(pos0),
+                                    out.ctypes.data_as(FP) if want_logits else None), self.h)
+        return self._logits.copy() if want_logits else None
 
     def logits_buffer(self):
         """The library's pinned logits buffer as a numpy view (state.logits of the host, zero copy)."""

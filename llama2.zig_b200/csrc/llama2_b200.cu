@@ -82,8 +82,8 @@ bool nccl_load(std::string *err) {
 // ---------------------------------------------------------------------------------------
 // Context (one rank)
 // ---------------------------------------------------------------------------------------
-enum StepMode { MODE_LOGITS = 0, MODE_ARGMAX = 1, MODE_SAMPLE = 2 };
-enum GraphId { G_LOGITS = 0, G_ARGMAX_ONE = 1, G_ARGMAX_LOOP = 2, G_SAMPLE = 3, G_COUNT = 4 };
+enum StepMode { MODE_LOGITS = 0, MODE_ARGMAX = 1, MODE_SAMPLE = 2, MODE_NOCLS = 3 };
+enum GraphId { G_LOGITS = 0, G_ARGMAX_ONE = 1, G_ARGMAX_LOOP = 2, G_SAMPLE = 3, G_PREFILL_LOOP = 4, G_COUNT = 5 };
 constexpr int kCandCap = 8192;               // top-p candidates returned per step (more => host filters itself)
 
 struct l2b_ctx {
@@ -827,6 +827,10 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, StepMode mode) {
         rc = residual_gemv(d, Xc, 2 * l + 1, "w2", l);
         if (rc) return rc;
     }
+    if (mode == MODE_NOCLS) {   // prompt prefill: the logits of this position are never looked at (:996-1000)
+        ctx->final_X = Xc;
+        return L2B_OK;
+    }
     // ---- final rmsnorm + classifier (:426-429)
     GemvParams k{};
     k.ctl = ctx->ctl;
@@ -894,9 +898,11 @@ int launch_sample_prep(l2b_ctx *ctx, cudaStream_t st) {
 // everything one call needs, as it is captured into (or eagerly enqueued instead of) graph `which`
 int enqueue_call(l2b_ctx *ctx, cudaStream_t st, int which) {
     const bool sink = !ctx->leader || ctx->rank == 0;   // in-process group: only rank 0 returns data to the host
-    if (which != G_ARGMAX_LOOP)
+    const bool loop = (which == G_ARGMAX_LOOP || which == G_PREFILL_LOOP);   // (token, pos) advance on the device
+    if (!loop)
         L2B_CUDA(ctx, cudaMemcpyAsync(ctx->ctl, ctx->h_ctl, CTL_HOST_WORDS * sizeof(int), cudaMemcpyHostToDevice, st));
-    const StepMode mode = (which == G_LOGITS) ? MODE_LOGITS : (which == G_SAMPLE) ? MODE_SAMPLE : MODE_ARGMAX;
+    const StepMode mode = (which == G_LOGITS) ? MODE_LOGITS : (which == G_SAMPLE) ? MODE_SAMPLE
+                          : (which == G_PREFILL_LOOP) ? MODE_NOCLS : MODE_ARGMAX;
     int rc = enqueue_step(ctx, st, mode);
     if (rc) return rc;
     const size_t vbytes = (size_t)ctx->cfg.vocab_size * sizeof(float);
@@ -918,12 +924,16 @@ int enqueue_call(l2b_ctx *ctx, cudaStream_t st, int which) {
         if (rc) return rc;
         if (sink) L2B_CUDA(ctx, cudaMemcpyAsync(ctx->h_ints, ctx->gen_out, sizeof(int), cudaMemcpyDeviceToHost, st));
         break;
+    case G_PREFILL_LOOP:   // every next token is forced: no argmax to exchange
+        rc = launch_advance(ctx, st, true, false);
+        if (rc) return rc;
+        break;
     default:   // G_ARGMAX_LOOP
         rc = launch_advance(ctx, st, true, ctx->world > 1 && ctx->use_p2p);
         if (rc) return rc;
         break;
     }
-    if (which != G_ARGMAX_LOOP)
+    if (!loop)
         L2B_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctl + CTL_WORDS, ctx->ctl, CTL_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
     return L2B_OK;
 }
@@ -1210,7 +1220,7 @@ int warm_up(const std::vector<l2b_ctx *> &ranks) {
             memset(ctx->h_ctl, 0, CTL_WORDS * sizeof(int));
             ctx->h_ctl[CTL_TEMP] = 0x3f800000;   // 1.0f
             ctx->h_ctl[CTL_TOPP] = 0x3f666666;   // 0.9f
-            if (which == G_ARGMAX_LOOP)
+            if (which == G_ARGMAX_LOOP || which == G_PREFILL_LOOP)
                 L2B_TRY(cuda_try(ctx, cudaMemcpyAsync(ctx->ctl, ctx->h_ctl, CTL_HOST_WORDS * sizeof(int), cudaMemcpyHostToDevice, ctx->stream), "ctl upload"));
             L2B_TRY(enqueue_call(ctx, ctx->stream, which));
         }
@@ -1218,7 +1228,7 @@ int warm_up(const std::vector<l2b_ctx *> &ranks) {
             L2B_TRY(cuda_try(ctx, cudaSetDevice(ctx->device), "cudaSetDevice"));
             L2B_TRY(cuda_try(ctx, cudaStreamSynchronize(ctx->stream), "warm-up step"));
             L2B_TRY(cuda_try(ctx, cudaGetLastError(), "warm-up step"));
-            if (ctx->h_ctl[CTL_WORDS + CTL_ERR] && which != G_ARGMAX_LOOP) {
+            if (ctx->h_ctl[CTL_WORDS + CTL_ERR] && which != G_ARGMAX_LOOP && which != G_PREFILL_LOOP) {
                 ctx->err = "tensor-parallel warm-up step timed out waiting for a peer";
                 g_create_error = ctx->err;
                 return L2B_ERR_COMM;
@@ -1577,17 +1587,11 @@ int32_t l2b_forward_sample(l2b_ctx *ctx, int32_t token, int32_t pos, float tempe
     return L2B_OK;
 }
 
-int32_t l2b_generate_argmax(l2b_ctx *ctx, int32_t token, int32_t pos, int32_t n_steps,
-                            const int32_t *forced, int32_t stop_on_bos, int32_t *out_next,
-                            int32_t *n_done) {
-    int rc = check_step_args(ctx, token, pos);
-    if (rc) return rc;
-    if (!out_next || !n_done || n_steps < 0) return fail(ctx, L2B_ERR_INVALID_ARG, "bad generate arguments");
-    if (n_steps > ctx->cfg.seq_len - pos) n_steps = ctx->cfg.seq_len - pos;   // :992-993
-    *n_done = 0;
-    if (n_steps == 0) return L2B_OK;
+// n_steps replays of a device-loop graph (G_ARGMAX_LOOP or G_PREFILL_LOOP) starting at (token, pos)
+static int run_device_loop(l2b_ctx *ctx, int which, int token, int pos, int n_steps, const int32_t *forced,
+                           int stop_on_bos, int *done_out) {
     std::vector<l2b_ctx *> ranks = locals(ctx);
-    int launches = 0;
+    int launches = 0, rc;
     for (l2b_ctx *c : ranks) {
         L2B_CUDA(ctx, cudaSetDevice(c->device));
         // forced tokens (prompt forcing, :999-1000); -1 = free-running
@@ -1607,11 +1611,11 @@ int32_t l2b_generate_argmax(l2b_ctx *ctx, int32_t token, int32_t pos, int32_t n_
         for (l2b_ctx *c : ranks) {
             if (ranks.size() > 1) L2B_CUDA(ctx, cudaSetDevice(c->device));
             if (c->use_graphs) {
-                L2B_CUDA(ctx, cudaGraphLaunch(c->graphs[G_ARGMAX_LOOP], c->stream));
-                if (c == ctx) launches += c->launches_per_step + 1;
+                L2B_CUDA(ctx, cudaGraphLaunch(c->graphs[which], c->stream));
+                if (c == ctx) launches += c->launches_per_step + (which == G_PREFILL_LOOP ? 0 : 1);
             } else {
                 c->last_launches = 0;
-                rc = enqueue_call(c, c->stream, G_ARGMAX_LOOP);
+                rc = enqueue_call(c, c->stream, which);
                 if (rc) { ctx->err = c->err; return rc; }
                 if (c == ctx) launches += c->last_launches;
             }
@@ -1631,11 +1635,52 @@ int32_t l2b_generate_argmax(l2b_ctx *ctx, int32_t token, int32_t pos, int32_t n_
     if (rc) return rc;
     L2B_CUDA(ctx, cudaSetDevice(ctx->device));
     L2B_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
-    const int done = ctx->h_ints[1];
+    *done_out = ctx->h_ints[1];
+    ctx->last_launches = launches;
+    if (pos + *done_out > ctx->n_appended) ctx->n_appended = pos + *done_out;
+    return L2B_OK;
+}
+
+int32_t l2b_generate_argmax(l2b_ctx *ctx, int32_t token, int32_t pos, int32_t n_steps,
+                            const int32_t *forced, int32_t stop_on_bos, int32_t *out_next,
+                            int32_t *n_done) {
+    int rc = check_step_args(ctx, token, pos);
+    if (rc) return rc;
+    if (!out_next || !n_done || n_steps < 0) return fail(ctx, L2B_ERR_INVALID_ARG, "bad generate arguments");
+    if (n_steps > ctx->cfg.seq_len - pos) n_steps = ctx->cfg.seq_len - pos;   // :992-993
+    *n_done = 0;
+    if (n_steps == 0) return L2B_OK;
+    int done = 0;
+    rc = run_device_loop(ctx, G_ARGMAX_LOOP, token, pos, n_steps, forced, stop_on_bos, &done);
+    if (rc) return rc;
     for (int i = 0; i < done; ++i) out_next[i] = ctx->h_gen[i];
     *n_done = done;
-    ctx->last_launches = launches;
-    if (pos + done > ctx->n_appended) ctx->n_appended = pos + done;
+    return L2B_OK;
+}
+
+// Prompt prefill (src/main.zig:996-1000 feeds prompt tokens through transformer() one
+// at a time and throws their logits away).  All positions run back to back on the device with
+// the next token forced, the classifier (60 % of stories15M's bytes) is skipped for every position
+// whose logits nobody reads, and no position pays a host round trip; the arithmetic per position
+// is the decode step's own, so the KV cache and any later logits are bit-identical to n calls of
+// l2b_forward.
+int32_t l2b_prefill(l2b_ctx *ctx, const int32_t *tokens, int32_t n_tokens, int32_t pos0, float *host_logits) {
+    if (!ctx || !tokens || n_tokens <= 0) return fail(ctx, L2B_ERR_INVALID_ARG, "bad prefill arguments");
+    int rc = check_step_args(ctx, tokens[0], pos0);
+    if (rc) return rc;
+    if (pos0 + n_tokens > ctx->cfg.seq_len) return fail(ctx, L2B_ERR_INVALID_ARG, "prompt runs past seq_len");
+    for (int i = 0; i < n_tokens; ++i)
+        if (tokens[i] < 0 || tokens[i] >= ctx->cfg.vocab_size) return fail(ctx, L2B_ERR_INVALID_ARG, "token out of range");
+    const int n_silent = host_logits ? n_tokens - 1 : n_tokens;   // positions whose logits are dropped
+    if (n_silent > 0) {
+        std::vector<int32_t> forced(n_silent);
+        for (int i = 0; i < n_silent; ++i) forced[i] = tokens[i + 1 < n_tokens ? i + 1 : i];
+        int done = 0;
+        rc = run_device_loop(ctx, G_PREFILL_LOOP, tokens[0], pos0, n_silent, forced.data(), 0, &done);
+        if (rc) return rc;
+        if (done != n_silent) return fail(ctx, L2B_ERR_STATE, "prefill stopped early");
+    }
+    if (host_logits) return l2b_forward(ctx, tokens[n_tokens - 1], pos0 + n_tokens - 1, host_logits);
     return L2B_OK;
 }
 

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <chrono>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 // ---------------------------------------------------------------------------------------
@@ -50,6 +51,9 @@ struct l2h_tokenizer {
     std::vector<std::string> tokens;
     std::vector<float> scores;
     uint32_t max_token_len = 0;
+    // the reference's lookup is an O(vocab) scan per merge candidate (:208-215, the
+    // author's TODO); same answers (FIRST id of a duplicated string) from a hash map
+    std::unordered_map<std::string, int32_t> first_id;
 };
 
 extern "C" int32_t l2h_tokenizer_load(const char *path, int32_t vocab_size, l2h_tokenizer **out) {
@@ -70,6 +74,8 @@ extern "C" int32_t l2h_tokenizer_load(const char *path, int32_t vocab_size, l2h_
     }
     fclose(f);
     if (!ok) { delete t; return L2B_ERR_INVALID_ARG; }
+    t->first_id.reserve((size_t)vocab_size * 2);
+    for (int i = 0; i < vocab_size; ++i) t->first_id.emplace(t->tokens[i], i);   // emplace keeps the first
     *out = t;
     return L2B_OK;
 }
@@ -80,11 +86,10 @@ extern "C" const char *l2h_tokenizer_token(const l2h_tokenizer *t, int32_t id, i
     if (len) *len = (int32_t)t->tokens[id].size();
     return t->tokens[id].data();
 }
-// linear scan, first match wins (:208-215)
+// first match wins (:208-215); O(1) instead of the reference's linear scan
 extern "C" int32_t l2h_tokenizer_lookup(const l2h_tokenizer *t, const char *bytes, int32_t len) {
-    for (size_t i = 0; i < t->tokens.size(); ++i)
-        if ((int32_t)t->tokens[i].size() == len && memcmp(t->tokens[i].data(), bytes, len) == 0) return (int32_t)i;
-    return -1;
+    auto it = t->first_id.find(std::string(bytes, (size_t)len));
+    return it == t->first_id.end() ? -1 : it->second;
 }
 
 static int utf8_len(unsigned char c) {
@@ -198,6 +203,17 @@ extern "C" int32_t l2h_sample_top_p(const float *logits, int32_t n, float p, voi
     return (int32_t)idx[cutoff_index].index;
 }
 
+extern "C" int32_t l2h_sample_top_p_candidates(l2b_prob_index *cand, int32_t m, float p) {
+    std::sort(cand, cand + m, [](const l2b_prob_index &a, const l2b_prob_index &b) { return a.prob > b.prob; });   // :771
+    float cumulative = 0.0f;
+    int32_t cutoff_index = m - 1;
+    for (int32_t i = 0; i < m; ++i) { cumulative += cand[i].prob; if (cumulative > p) { cutoff_index = i; break; } }   // :774-781
+    const float r = next_f32() * cumulative;                                                                        // :785
+    float cdf = 0.0f;
+    for (int32_t i = 0; i <= cutoff_index; ++i) { cdf += cand[i].prob; if (r < cdf) return cand[i].index; }
+    return cand[cutoff_index].index;
+}
+
 // <0xXX> raw byte tokens (:1055-1076)
 static int raw_byte(const char *s, int len) {
     if (len != 6 || s[0] != '<' || s[1] != '0' || s[2] != 'x' || s[5] != '>') return -1;
@@ -238,9 +254,57 @@ extern "C" int32_t l2h_generate(l2b_ctx *ctx, const l2b_config *cfg, const l2h_g
     clk::time_point t_first;
     const clk::time_point t_begin = clk::now();
     int pos = 0;
+    std::vector<l2b_prob_index> cand(8192);
+    auto print_token = [&](int32_t nx) {
+        if (tk) {                                                 // :1022-1034
+            int32_t len = 0;
+            const char *s = l2h_tokenizer_token(tk, nx, &len);
+            if (s) {
+                if (token == 1 && len > 0 && s[0] == ' ') { ++s; --len; }
+                const int b = raw_byte(s, len);
+                if (b >= 0) fputc(b, stdout); else fwrite(s, 1, len, stdout);
+            }
+        }
+    };
+    if (opt->use_prefill && n_prompt > 0 && n_prompt < seq_len) {
+        // positions 0 .. n_prompt-1 hold BOS, prompt[0 .. n_prompt-2]; their logits are never read (:999-1000)
+        std::vector<int32_t> toks(n_prompt);
+        toks[0] = token;
+        for (int i = 1; i < n_prompt; ++i) toks[i] = prompt[i - 1];
+        const int32_t rc = l2b_prefill(ctx, toks.data(), n_prompt, 0, nullptr);
+        if (rc) return rc;
+        res->h2d_bytes += 4ull * n_prompt;
+        res->n_forward += n_prompt;
+        for (; pos < n_prompt; ++pos) {
+            next = prompt[pos];
+            if (out_tokens && res->n_tokens < cap) out_tokens[res->n_tokens++] = next;
+            print_token(next);
+            token = next;
+            if (!timer_started) { timer_started = true; t_first = clk::now(); }
+        }
+    }
     for (; pos < seq_len; ++pos) {                                // :995
         int32_t rc;
         const bool device_argmax = opt->use_device_argmax && opt->temperature == 0.0f && pos >= n_prompt;
+        const bool device_sampler = opt->use_device_sampler && opt->temperature != 0.0f && pos >= n_prompt;
+        if (device_sampler) {
+            int32_t n_cand = 0;
+            const bool filter = !(opt->top_p == 0.0f || opt->top_p == 1.0f);
+            rc = l2b_forward_sample(ctx, token, pos, opt->temperature, opt->top_p, logits.data(), cand.data(),
+                                    (int32_t)cand.size(), &n_cand);                        // :996 + :1005-1008 + :761-768
+            if (rc) return rc;
+            ++res->n_forward;
+            res->h2d_bytes += 16; res->d2h_bytes += (uint64_t)V * 4 + (filter ? 8192ull * 8 + 4 : 0);
+            if (!filter) next = l2h_sample(logits.data(), V);                              // :1010
+            else if (n_cand > 0) next = l2h_sample_top_p_candidates(cand.data(), n_cand, opt->top_p);   // :770-797
+            else next = l2h_sample_top_p(logits.data(), V, opt->top_p, indexed.data());     // too many candidates: host filters
+            if (out_tokens && res->n_tokens < cap) out_tokens[res->n_tokens++] = next;
+            if (opt->stop_on_bos && next == 1) break;
+            print_token(next);
+            token = next;
+            if (!timer_started) { timer_started = true; t_first = clk::now(); }
+            continue;
+        }
         if (device_argmax) {
             rc = l2b_forward_argmax(ctx, token, pos, &next);      // :996 + :1003 on device
             res->h2d_bytes += 8; res->d2h_bytes += 4;

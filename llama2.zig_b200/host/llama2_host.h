@@ -44,6 +44,8 @@ void l2h_softmax(float *x, int32_t n);                                          
 void l2h_seed(uint64_t seed);                                                              /* :845, :926 */
 int32_t l2h_sample(const float *probs, int32_t n);                                         /* :728-741 */
 int32_t l2h_sample_top_p(const float *probs, int32_t n, float p, void *scratch_2n_words);  /* :754-798 */
+/* :770-797 on a candidate list that already passed the cutoff of :761-768 (sorted here)      */
+int32_t l2h_sample_top_p_candidates(l2b_prob_index *cand, int32_t n_cand, float p);
 
 typedef struct l2h_gen_options {
     float temperature;      /* :840, 0 => argmax                                             */
@@ -52,6 +54,11 @@ typedef struct l2h_gen_options {
     int32_t stop_on_bos;    /* :1017-1019 (1 in the reference)                               */
     int32_t use_device_argmax; /* 0: l2b_forward + host sampler (reference data flow);
                                   1: l2b_forward_argmax (only the token id crosses PCIe)      */
+    int32_t use_prefill;       /* 1: the prompt positions go through l2b_prefill (no logits, no
+                                  host round trip per prompt token; :996-1000)                */
+    int32_t use_device_sampler;/* 1, temperature > 0: l2b_forward_sample does logits/=T, softmax and
+                                  the top-p prefilter on the GPU (:1005-1008, :761-768); the host
+                                  only sorts the candidates and draws (:770-797)               */
 } l2h_gen_options;
 
 typedef struct l2h_gen_result {

@@ -22,12 +22,16 @@ static const char *usage_text =
     " -s, --seed <int>          random seed, default to time\n"
     " -v, --verbose             print model info and tokens/s\n"
     " -z, --tokenizer <path>    path to the tokenizer to use, default to \"tokenizer.bin\"\n"
-    "     --device-argmax       with -t 0: argmax on the GPU, only the token id crosses PCIe\n";
+    "     --device-argmax       with -t 0: argmax on the GPU, only the token id crosses PCIe\n"
+    "     --device-sampler      with -t > 0: logits/T, softmax and the top-p prefilter on the GPU\n"
+    "     --prefill             prompt positions run on the GPU back to back (no logits, no host round trip)\n"
+    "     --gpus <1|2|4|8>      tensor-parallel over that many GPUs (llama2-7B class models)\n";
 
 int main(int argc, char **argv) {
     if (argc < 2) { fputs(usage_text, stdout); return 0; }
     const char *bin_path = nullptr, *input = nullptr, *tokenizer_path = "tokenizer.bin";
-    l2h_gen_options opt{1.0f, 0.9f, 0, 1, 0};
+    l2h_gen_options opt{1.0f, 0.9f, 0, 1, 0, 0, 0};
+    int n_gpus = 1;
     bool verbose = false;
     l2h_seed((uint64_t)time(nullptr));
     for (int i = 1; i < argc; ++i) {
@@ -48,6 +52,9 @@ int main(int argc, char **argv) {
         else if (a == "-s" || a == "--seed") l2h_seed(strtoull(need("seed"), nullptr, 10));
         else if (a == "-v" || a == "--verbose") verbose = true;
         else if (a == "--device-argmax") opt.use_device_argmax = 1;
+        else if (a == "--device-sampler") opt.use_device_sampler = 1;
+        else if (a == "--prefill") opt.use_prefill = 1;
+        else if (a == "--gpus") n_gpus = atoi(need("gpus"));
         else { fprintf(stderr, "error: unknown argument '%s'\n", argv[i]); fputs(usage_text, stdout); return 0; }
     }
     if (!bin_path) { fputs(usage_text, stdout); return 0; }
@@ -61,7 +68,7 @@ int main(int argc, char **argv) {
         fprintf(stderr, "shared weights: %s\ntemperature: %g\ntop-p: %g\n\n", c.shared_weights ? "true" : "false", opt.temperature, opt.top_p);
     }
     l2b_ctx *ctx = nullptr;
-    int32_t rc = l2b_create(&ctx, &c, ck.data, ck.n_floats, nullptr, nullptr, 1);   // after :967
+    int32_t rc = l2b_create(&ctx, &c, ck.data, ck.n_floats, nullptr, nullptr, n_gpus);   // after :967
     if (rc) { fprintf(stderr, "error: l2b_create: %s (%s)\n", l2b_status_string(rc), l2b_last_error(nullptr)); return 1; }
     l2h_free_checkpoint(&ck);   // host copy no longer needed: weights live in HBM
 

@@ -309,3 +309,32 @@ def test_logits_buffer_is_zero_copy_state_logits(l2b, stories15m):
             assert np.array_equal(own, buf)
         ms, nbytes = t.load_stats()
         assert nbytes == 60_816_028 - 28 - 4 * 2 * 256 * 24 and ms > 0      # freq_cis tables are not uploaded
+
+
+def test_prefill_equals_token_by_token(l2b, oracle, stories15m):
+    """l2b_prefill (all prompt positions on the device, classifier skipped where the
+    reference discards the logits, src/main.zig:996-1000) leaves the same KV cache and returns the
+    same logits as feeding the prompt through l2b_forward one token at a time — bit for bit."""
+    with open(os.path.join(GOLDEN, "stories15M_t0_tokens.json")) as f:
+        gold = json.load(f)["tokens"]
+    prompt = [1] + gold[:23]                      # BOS + 23 story tokens
+    ck = l2b.read_checkpoint(stories15m, mmap=False)
+    with l2b.Transformer(ck) as a, l2b.Transformer(ck) as b:
+        for pos, tok in enumerate(prompt):
+            want = a.forward(tok, pos)
+        got = b.prefill(prompt, 0)
+        assert np.array_equal(got, want)
+        assert int(np.argmax(got)) == gold[23]
+        n = 6 * 256 * 288
+        assert np.array_equal(a.state("key_cache")[:n], b.state("key_cache")[:n])
+        assert np.array_equal(a.state("value_cache")[:n], b.state("value_cache")[:n])
+        # continue decoding after a logits-free prefill of a longer prompt
+        b.reset()
+        assert b.prefill(prompt + gold[23:40], 0, want_logits=False) is None
+        for pos in range(len(prompt), len(prompt) + 17):
+            a.forward(gold[pos - 1], pos)
+        nxt_a = a.forward_argmax(gold[40], 41)
+        nxt_b = b.forward_argmax(gold[40], 41)
+        assert nxt_a == nxt_b == gold[41]
+        with pytest.raises(l2b.L2BError):
+            b.prefill([1] * 300, 0)               # runs past seq_len

@@ -79,3 +79,52 @@ def test_sampler_helpers(host):
     peaked = np.array([0.01, 0.97, 0.01, 0.01], dtype=np.float32)
     for _ in range(20):
         assert host.l2h_sample_top_p(peaked.ctypes.data_as(FP), 4, 0.9, scratch) == 1
+
+
+def test_tokenizer_hash_lookup_equals_first_match_scan(host):
+    """the O(1) lookup must answer exactly like the reference's linear scan (:208-215):
+    the FIRST id whose bytes match — the shipped vocabulary has 204 duplicated strings."""
+    path = tokenizer_path()
+    if path is None:
+        pytest.skip("tokenizer.bin not staged")
+    tk = C.c_void_p()
+    assert host.l2h_tokenizer_load(path.encode(), 32000, C.byref(tk)) == 0
+    first, dups = {}, 0
+    n = C.c_int32()
+    for i in range(32000):
+        p = host.l2h_tokenizer_token(tk, i, C.byref(n))
+        s = C.string_at(p, n.value)
+        if s in first:
+            dups += 1
+        first.setdefault(s, i)
+    assert dups == 204
+    for s, i in first.items():
+        assert host.l2h_tokenizer_lookup(tk, s, len(s)) == i
+    assert host.l2h_tokenizer_lookup(tk, b"\xff\xfe-not-a-token", 14) == -1
+    host.l2h_tokenizer_free(tk)
+
+
+def test_top_p_on_prefiltered_candidates_equals_full_sampler(host):
+    """The host half of the split sampler (:770-797 on the device's candidate list) picks the same
+    token as sample_top_p on the full distribution (:752-798) for the same PRNG state."""
+    FP = C.POINTER(C.c_float)
+
+    class PI(C.Structure):
+        _fields_ = [("prob", C.c_float), ("index", C.c_int32)]
+
+    host.l2h_sample_top_p_candidates.argtypes = [C.POINTER(PI), C.c_int32, C.c_float]
+    rng = np.random.default_rng(3)
+    n, p = 32000, 0.9
+    for trial in range(20):
+        logits = (rng.standard_normal(n) * 3).astype(np.float32)
+        probs = np.exp(logits - logits.max()).astype(np.float32)
+        probs /= probs.sum(dtype=np.float32)
+        cutoff = np.float32((np.float32(1) - np.float32(p)) / (np.float32(n) - np.float32(1)))
+        keep = np.nonzero(probs >= cutoff)[0]
+        cand = (PI * keep.size)(*[PI(float(probs[i]), int(i)) for i in keep])
+        scratch = (C.c_uint64 * n)()
+        host.l2h_seed(100 + trial)
+        a = host.l2h_sample_top_p(probs.ctypes.data_as(FP), n, p, scratch)
+        host.l2h_seed(100 + trial)
+        b = host.l2h_sample_top_p_candidates(cand, keep.size, p)
+        assert a == b
