@@ -259,6 +259,7 @@ struct GemvParams {
     unsigned long long *amax;  // ARGMAX: packed running maximum (must be 0 before the launch)
     int row_base;              // ARGMAX / XCHG: global index of out row 0 (vocab shard offset)
     int nstage;                // gemv_tma_kernel: ring depth (2..TMA_MAX_STAGES)
+    int nprefill;              // gemv_tma_kernel: stages put in flight BEFORE the dependency wait (1..nstage)
     // ---- tensor-parallel exchange (fused GEMV + all-reduce over peer memory); unused when xworld == 0
     // producer side (EPI_XCHG): row v of my result goes, as an LL unit, to ll_out[d][row_base + v]
     // for every destination d < ll_ndst (the landing area reserved for MY rank on that peer)
@@ -825,7 +826,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
         // the other warps must not meet it at a barrier (measured r02: with the producer inside the
         // prologue's barriers the activation vector was staged 5.3 us after the dependency wait, and
         // the memory pipe sat idle behind a full ring).
-        while (p_it < total && p_it < NSTAGE) produce_one();
+        // Only nprefill stages go out before the wait: the activation vector's bulk copy is issued by
+        // warp 0 right after the wait and is served behind everything this SM already requested
+        // (~47 GB/s of HBM per SM: a full 192 KB ring ahead of it costs 4 us).
+        while (p_it < total && p_it < p.nprefill) produce_one();
         if (p_it >= total) pdl_launch_dependents();
         if (lane == 0) L2B_STAMP(p.trace, 1);
         pdl_wait();
@@ -860,7 +864,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
     if (p.ctl[CTL_DONE]) {
         // generation already ended: drain the bulk copies already aimed at our shared memory
         if (tid == 0)
-            for (int s = 0; s < NSTAGE && s < total; ++s) mbar_wait(&full[s], 0);
+            for (int s = 0; s < p.nprefill && s < total; ++s) mbar_wait(&full[s], 0);
         __syncthreads();
         return;
     }
@@ -877,11 +881,18 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
             mbar_expect_tx(&xbar, bytes);
             tma_load_1d(xs, xsrc, bytes, &xbar);
         }
-        if (EPI == EPI_QKV && tid >= NT + 32) {          // epilogue warp: this position's RoPE row
+        // epilogue warp: this position's RoPE row.  The table row comes from DRAM on big models (the
+        // weight stream evicts it), so it is only FETCHED here, into registers; it is parked in shared
+        // memory after the prologue's last barrier — the other warps must not wait for it
+        // (measured r02: it held the qkv prologue 1.4 us longer than the w13 one)
+        float rc_reg[4], rs_reg[4];
+        if (EPI == EPI_QKV && tid >= NT + 32) {
             const int half = p.head_size >> 1;
-            for (int i = lane; i < half; i += 32) {
-                rope_s[0][i] = p.rope_cos[(size_t)pos * half + i];
-                rope_s[1][i] = p.rope_sin[(size_t)pos * half + i];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = lane + 32 * k;
+                rc_reg[k] = (i < half) ? __ldg(p.rope_cos + (size_t)pos * half + i) : 0.0f;
+                rs_reg[k] = (i < half) ? __ldg(p.rope_sin + (size_t)pos * half + i) : 0.0f;
             }
         }
         mbar_wait(&xbar, 0);
@@ -922,6 +933,15 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
             }
         }
         named_bar_sync(1, PRO_THREADS);
+        if (EPI == EPI_QKV && tid >= NT + 32) {
+            const int half = p.head_size >> 1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = lane + 32 * k;
+                if (i < half) { rope_s[0][i] = rc_reg[k]; rope_s[1][i] = rs_reg[k]; }
+            }
+            __syncwarp();
+        }
     }
     if (tid == 0) L2B_STAMP(p.trace, 3);
 

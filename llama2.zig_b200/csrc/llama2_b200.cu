@@ -150,6 +150,7 @@ struct l2b_ctx {
     int trace_launches = 0;
     int tma_ctas_per_sm = 1;
     int tma_stages = 0;                      // 0 = auto; else forced ring depth
+    int tma_prefill = 0;                     // stages in flight before the dependency wait; 0 = the whole ring (L2B_TMA_PREFILL)
     bool big_kernel_tma = true;              // bandwidth-bound GEMVs: TMA-ring kernel (false: register-fed 8-row kernel)
     long long gemv8_min_bytes = 8ll << 20;   // >= this many weight bytes (and n >= big_min_n): streaming kernel; -1 = never
     int big_min_n = 1024;                    // measured r02: at n = 768 the TMA ring (192 of 256 columns per stage) loses to the latency kernel
@@ -497,6 +498,7 @@ int launch_gemv(l2b_ctx *ctx, int epi, const GemvParams &p, cudaStream_t st, con
     lc.numAttrs = ctx->use_pdl ? 1 : 0;
     GemvParams pp = p;
     pp.nstage = nstage;
+    pp.nprefill = (ctx->tma_prefill > 0 && ctx->tma_prefill < nstage) ? ctx->tma_prefill : nstage;
     pp.spin_ns = ctx->spin_ns;
     pp.trace = trace_slot(ctx);
     ctx->last_grid = grid;
@@ -1190,6 +1192,8 @@ int create_rank(l2b_ctx *ctx, const l2b_config *cfg, const Source &src, const fl
         if (env5) ctx->tma_stages = atoi(env5);
         const char *enva = getenv("L2B_ATTN");
         if (enva && strcmp(enva, "3pass") == 0) ctx->attn_flash = false;
+        const char *envpf = getenv("L2B_TMA_PREFILL");
+        if (envpf) ctx->tma_prefill = atoi(envpf);
         const char *envs = getenv("L2B_SPIN_TIMEOUT_MS");
         if (envs && atoll(envs) > 0) ctx->spin_ns = (unsigned long long)atoll(envs) * 1000000ull;
         const char *envt = getenv("L2B_TRACE");

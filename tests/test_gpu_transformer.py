@@ -281,11 +281,14 @@ def test_forward_sample_matches_host_sampler_steps(l2b, oracle, stories15m):
             ref64 = np.exp(want.astype(np.float64) - want.max())
             ref64 /= ref64.sum()
             lib.orc_softmax(want.ctypes.data_as(FP), want.size)
-            # the reference sums the 32000 exponentials sequentially in fp32 (:697-701): that sum itself is
-            # only good to ~1e-4, the device's tree sum to ~1e-7, so the bar against the restatement is
-            # 3e-4 and the bar against the exact softmax is the north star's 1e-4
-            assert np.max(np.abs(probs - want)) <= 3e-4 * np.max(want)
+            # The bar is the exact softmax (1e-4, the north star's tolerance).  The reference itself sums the
+            # 32000 exponentials sequentially in fp32 (:697-701): once the running sum has absorbed the
+            # dominant term (~1.0), terms below its half-ulp (6e-8) are rounded away one by one, so on a sharp
+            # distribution (T = 0.5: p_max = 0.985, the other 31999 terms share 0.015) its normalisation is
+            # off by ~1e-3.  The device's tree sum does not reproduce that loss; against the restatement the
+            # bar is therefore 2e-3, and the argmax / candidate set are compared exactly below.
             assert np.max(np.abs(probs - ref64)) <= 1e-4 * np.max(ref64)
+            assert np.max(np.abs(probs - want)) <= 2e-3 * np.max(want)
             assert int(np.argmax(probs)) == nxt
             if top_p in (0.0, 1.0):
                 assert cand is None
