@@ -107,6 +107,9 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_release_gpu(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_global() {
     asm volatile("fence.proxy.async.global;" ::: "memory");
 }
@@ -267,7 +270,7 @@ struct GemvParams {
     int ll_ndst;
     // consumer side (fused-rmsnorm kernels): x_in is the residual stream; before staging it, the
     // partial rows of all xworld ranks (ll_in[r * n + i]) are added into it, slice by slice, by the
-    // first ceil(n/128) CTAs; rdone counts finished slices (monotonic: epoch * slices when complete)
+    // first ceil(n/128) CTAs; rdone[s] = epoch once slice s of this step has been folded into x
     const unsigned long long *ll_in;
     unsigned int *rdone;
     int xworld;
@@ -296,8 +299,9 @@ __device__ __forceinline__ const float *gemv_row_ptr(const GemvParams &p, int v)
 //   x[i] += sum_r partial_r[i]   (fixed rank order: every rank forms bit-identical x)
 // Work is cut into slices of 32 float4; slice s belongs to warp 0 of CTA (s mod grid), which polls
 // the LL units of that slice (they arrive straight from the producers' epilogues over NVLink),
-// writes the new x slice and bumps `rdone`.  Every CTA then waits until all slices of this step are
-// done, so the 148 CTAs read 16 KB of finished x instead of 148 x g x 16 KB of partials.
+// writes the new x slice and stamps rdone[s] with the epoch.  Every CTA then waits until all slice
+// flags carry this step's epoch, so the 148 CTAs read 16 KB of finished x instead of 148 x g x 16 KB
+// of partials.
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -331,14 +335,15 @@ __device__ __forceinline__ void tp_reduce_into_x(const GemvParams &p, int bar_id
             }
             __threadfence();
             __syncwarp();
-            if (lane == 0) atomicAdd(p.rdone, 1u);
+            if (lane == 0) st_release_gpu(p.rdone + s, epoch);   // slice s of this step is in x
         }
-        if (lane == 0) {
-            const unsigned int want = epoch * (unsigned int)nslices;
-            while ((int)(ld_acquire_gpu(p.rdone) - want) < 0)
+        // every slice flag must carry THIS step's epoch (flags, not a counter: a step that skips a
+        // reduce point - prompt prefill skips the classifier - must not shift the expected value)
+        for (int s = lane; s < nslices; s += 32)
+            while (ld_acquire_gpu(p.rdone + s) != epoch)
                 if (sg.expired()) break;
-            fence_proxy_async_global();   // x is about to be read through the TMA (async proxy)
-        }
+        __syncwarp();
+        if (lane == 0) fence_proxy_async_global();   // x is about to be read through the TMA (async proxy)
     }
     named_bar_sync(bar_id, bar_threads);
 }

@@ -138,7 +138,7 @@ struct l2b_ctx {
     //   ll_red    [2L reduce points][world source ranks][dim] LL units   (wo / w2 partial rows)
     //   ll_logits [vocab] LL units                                       (classifier slices of all ranks)
     //   ll_amax   [world][2] LL units                                    (packed argmax keys)
-    //   rdone     [2L] slice counters (local use only)
+    //   rdone     [2L][dim/128] slice flags (local use only)
     bool use_p2p = false;
     unsigned char *arena = nullptr;
     size_t arena_bytes = 0, off_red = 0, off_logits = 0, off_amax = 0, off_rdone = 0;
@@ -664,8 +664,9 @@ unsigned long long *ll_logits_at(unsigned char *arena, const l2b_ctx *c) {
 unsigned long long *ll_amax_at(unsigned char *arena, const l2b_ctx *c, int src_rank) {
     return reinterpret_cast<unsigned long long *>(arena + c->off_amax) + 2 * (size_t)src_rank;
 }
+int tp_slices(const l2b_ctx *c) { return (c->dim / 4 + TP_SLICE4 - 1) / TP_SLICE4; }
 unsigned int *rdone_at(const l2b_ctx *c, int slot) {
-    return reinterpret_cast<unsigned int *>(c->arena + c->off_rdone) + slot;
+    return reinterpret_cast<unsigned int *>(c->arena + c->off_rdone) + (size_t)slot * tp_slices(c);
 }
 
 int launch_small(l2b_ctx *ctx, const void *fn, dim3 grid, dim3 block, void **args, cudaStream_t st, bool pdl) {
@@ -1172,7 +1173,7 @@ int create_rank(l2b_ctx *ctx, const l2b_config *cfg, const Source &src, const fl
         ctx->off_logits = o; o += (size_t)V * sizeof(unsigned long long);
         ctx->off_amax = o;   o += (size_t)world * 2 * sizeof(unsigned long long);
         o = (o + 255) & ~(size_t)255;
-        ctx->off_rdone = o;  o += slots * sizeof(unsigned int);
+        ctx->off_rdone = o;  o += slots * (size_t)tp_slices(ctx) * sizeof(unsigned int);
         ctx->arena_bytes = (o + 255) & ~(size_t)255;
         L2B_TRY(dev_alloc(ctx, &ctx->arena, ctx->arena_bytes));
         L2B_TRY(cuda_try(ctx, cudaMemsetAsync(ctx->arena, 0, ctx->arena_bytes, ctx->stream), "memset"));

@@ -2,6 +2,10 @@
 
   python scripts/summarize_ncu.py launches gpurun_out/launches_X.csv   > profiles/rNN_launches_X.md
   python scripts/summarize_ncu.py full     gpurun_out/prof_X.ncu-rep   > profiles/rNN_ncu_X.md
+  python scripts/summarize_ncu.py traffic  gpurun_out/prof_X.ncu-rep WORKLOAD LABEL 'REGEX' SHA16 profiles/rNN_traffic.json
+      (adds dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels matching REGEX as
+       WORKLOAD/LABEL, tagged with the kernel-source sha the capture was built from: bench.py only
+       reports roofline.traffic when that sha equals the running build's)
 """
 import collections
 import csv
@@ -79,5 +83,32 @@ def full(path):
         print(f"| {i} | `{r[h.index('Kernel Name')][:60]}` | {r[h.index('Grid Size')]} | " + " | ".join(cells) + f" | {stalls} |")
 
 
+def traffic(path, workload, label, regex, sha, out_json):
+    import json
+    import os
+    import re
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    h = rows[0]
+    ki, ri, wi = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+    units = rows[1]
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = []
+    for r in rows[2:]:
+        if re.search(regex, r[ki]):
+            vals.append(float(r[ri].replace(",", "")) * mult[units[ri]] + float(r[wi].replace(",", "")) * mult[units[wi]])
+    assert vals, f"no kernel matches {regex}"
+    rec = json.load(open(out_json)) if os.path.exists(out_json) else {}
+    if rec.get("kernel_source_sha16") != sha:
+        rec = {"kernel_source_sha16": sha}
+    rec.setdefault(workload, {})[label] = {"traffic": sum(vals) / len(vals), "launches": len(vals),
+                                           "source": f"ncu --set full, {os.path.basename(path)}, kernels /{regex}/"}
+    json.dump(rec, open(out_json, "w"), indent=1)
+    print(workload, label, rec[workload][label])
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:8])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
