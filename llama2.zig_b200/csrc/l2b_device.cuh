@@ -263,16 +263,16 @@ struct GemvParams {
     int row_base;              // ARGMAX / XCHG: global index of out row 0 (vocab shard offset)
     int nstage;                // gemv_tma_kernel: ring depth (2..TMA_MAX_STAGES)
     int nprefill;              // gemv_tma_kernel: stages put in flight BEFORE the dependency wait (1..nstage)
-    // ---- tensor-parallel exchange (fused GEMV + all-reduce over peer memory); unused when xworld == 0
-    // producer side (EPI_XCHG): row v of my result goes, as an LL unit, to ll_out[d][row_base + v]
-    // for every destination d < ll_ndst (the landing area reserved for MY rank on that peer)
+    // ---- tensor-parallel exchange (fused GEMV + all-reduce over peer memory); unused when ll_ndst == 0
+    // EPI_XCHG: row v of my result goes, as an LL unit, to ll_out[d][row_base + v] for every
+    // destination d < ll_ndst (the landing area reserved for MY rank on that peer).
     unsigned long long *ll_out[MAX_TP];
     int ll_ndst;
-    // consumer side (fused-rmsnorm kernels): x_in is the residual stream; before staging it, the
-    // partial rows of all xworld ranks (ll_in[r * n + i]) are added into it, slice by slice, by the
-    // first ceil(n/128) CTAs; rdone[s] = epoch once slice s of this step has been folded into x
+    // All-reduce tail (wo / w2; xres != nullptr): once a CTA has sent its own rows, CTA s < ceil(rows/128)
+    // folds slice s of ALL ranks' partial rows (ll_in[r * total_rows + i], they arrive straight from
+    // the other CTAs' / other GPUs' epilogues) into the residual stream: xres[i] += sum_r partial_r[i].
     const unsigned long long *ll_in;
-    unsigned int *rdone;
+    float *xres;
     int xworld;
     int bump_epoch;            // set on the first kernel of a step: CTA 0 increments ctl[CTL_EPOCH]
     unsigned long long spin_ns;  // bound on every peer wait (SpinGuard)
@@ -294,58 +294,43 @@ __device__ __forceinline__ const float *gemv_row_ptr(const GemvParams &p, int v)
     }
 }
 
-// ---- tensor-parallel all-reduce, consumer half.  Called by every thread of a fused-rmsnorm
-// kernel after griddepcontrol.wait.  The residual stream x (p.x_in) is updated IN PLACE:
+// ---- tensor-parallel all-reduce, second half, run by ONE warp of a wo / w2 CTA after that CTA has
+// sent its own partial rows.  The residual stream x is updated IN PLACE:
 //   x[i] += sum_r partial_r[i]   (fixed rank order: every rank forms bit-identical x)
-// Work is cut into slices of 32 float4; slice s belongs to warp 0 of CTA (s mod grid), which polls
-// the LL units of that slice (they arrive straight from the producers' epilogues over NVLink),
-// writes the new x slice and stamps rdone[s] with the epoch.  Every CTA then waits until all slice
-// flags carry this step's epoch, so the 148 CTAs read 16 KB of finished x instead of 148 x g x 16 KB
-// of partials.
+// Work is cut into slices of 32 float4; slice s belongs to CTA (s mod grid), which polls the LL units
+// of that slice — they arrive straight from the epilogues of the CTAs (local and, over NVLink,
+// remote) that own those rows — and writes the new x slice.  Kernel completion then means "x is
+// reduced", so the consumer kernel's prologue is the single-GPU one and stages 16 KB of finished x
+// instead of g x 16 KB of partials.  Doing this at the TAIL of the producer rather than in the
+// consumer's prologue matters: measured (r02, 2 GPUs), loads issued from a CTA whose TMA ring is
+// pre-filling wait ~4 us behind the 192 KB that SM already requested.
+constexpr int TP_SLICE4 = 32;
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-constexpr int TP_SLICE4 = 32;
-// bar_id / bar_threads: the barrier every caller passes through at the end (0, blockDim for the
-// block-structured kernels; the TMA kernel's prologue runs without its producer warp)
-__device__ __forceinline__ void tp_reduce_into_x(const GemvParams &p, int bar_id, int bar_threads) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int n4 = p.n >> 2;
+__device__ __forceinline__ void tp_reduce_tail(const GemvParams &p, unsigned int epoch, int lane) {
+    const int n4 = p.total_rows >> 2;
     const int nslices = (n4 + TP_SLICE4 - 1) / TP_SLICE4;
-    const unsigned int epoch = (unsigned int)p.ctl[CTL_EPOCH];
-    if (tid < 32) {
-        SpinGuard sg = spin_guard(p.ctl, p.spin_ns);
-        float4 *x4 = reinterpret_cast<float4 *>(const_cast<float *>(p.x_in));
-        for (int s = blockIdx.x; s < nslices; s += gridDim.x) {
-            const int i = s * TP_SLICE4 + lane;
-            if (i < n4) {
-                float4 v = __ldcg(x4 + i);
-                for (int r = 0; r < p.xworld; ++r) {
-                    const unsigned long long *u = p.ll_in + (size_t)r * p.n + (size_t)i * 4;
-                    uint4 a = ll_load2(u), b = ll_load2(u + 2);
-                    while (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch) {
-                        if (sg.expired()) break;
-                        a = ll_load2(u);
-                        b = ll_load2(u + 2);
-                    }
-                    v.x += __uint_as_float(a.x); v.y += __uint_as_float(a.z);   // accum(), :708-713
-                    v.z += __uint_as_float(b.x); v.w += __uint_as_float(b.z);
+    SpinGuard sg = spin_guard(p.ctl, p.spin_ns);
+    float4 *x4 = reinterpret_cast<float4 *>(p.xres);
+    for (int s = blockIdx.x; s < nslices; s += gridDim.x) {
+        const int i = s * TP_SLICE4 + lane;
+        if (i < n4) {
+            float4 v = __ldcg(x4 + i);
+            for (int r = 0; r < p.xworld; ++r) {
+                const unsigned long long *u = p.ll_in + (size_t)r * p.total_rows + (size_t)i * 4;
+                uint4 a = ll_load2(u), b = ll_load2(u + 2);
+                while (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch) {
+                    if (sg.expired()) break;
+                    a = ll_load2(u);
+                    b = ll_load2(u + 2);
                 }
-                __stcg(x4 + i, v);
+                v.x += __uint_as_float(a.x); v.y += __uint_as_float(a.z);   // accum(), :708-713
+                v.z += __uint_as_float(b.x); v.w += __uint_as_float(b.z);
             }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) st_release_gpu(p.rdone + s, epoch);   // slice s of this step is in x
+            __stcg(x4 + i, v);
         }
-        // every slice flag must carry THIS step's epoch (flags, not a counter: a step that skips a
-        // reduce point - prompt prefill skips the classifier - must not shift the expected value)
-        for (int s = lane; s < nslices; s += 32)
-            while (ld_acquire_gpu(p.rdone + s) != epoch)
-                if (sg.expired()) break;
-        __syncwarp();
-        if (lane == 0) fence_proxy_async_global();   // x is about to be read through the TMA (async proxy)
     }
-    named_bar_sync(bar_id, bar_threads);
 }
 
 // ---- shared prologue: stage the activation vector (+ rmsnorm) into shared memory.
@@ -354,7 +339,6 @@ __device__ __forceinline__ void gemv_stage_input(const GemvParams &p, float *xs,
                                                  uint64_t *bar, float *scratch) {
     const int tid = threadIdx.x;
     const int n4 = p.n >> 2;
-    if (p.ll_in) tp_reduce_into_x(p, 0, NT);
     const float *xsrc = p.emb ? p.emb + (size_t)p.ctl[CTL_TOKEN] * p.n : p.x_in;
     float *gs = aux;
     float *ps = p.gamma ? aux + p.n : aux;               // sum of the partial vectors (when p.parts)
@@ -612,6 +596,7 @@ __global__ void __launch_bounds__(NT) gemv_kernel(const GemvParams p) {
     }
     if (!triggered) pdl_launch_dependents();
     gemv_finish_argmax<EPI>(p, best, &blk_key);
+    if (EPI == EPI_XCHG && p.xres && tid < 32) tp_reduce_tail(p, epoch, tid);
 }
 
 // ---- v2: bandwidth-bound shapes (n >= 1024, many MB).  The whole CTA (256 threads) walks the
@@ -743,6 +728,7 @@ __global__ void __launch_bounds__(NT, 2) gemv8_kernel(const GemvParams p) {
     }
     if (!triggered) pdl_launch_dependents();
     gemv_finish_argmax<EPI>(p, best, &blk_key);
+    if (EPI == EPI_XCHG && p.xres && tid < 32) tp_reduce_tail(p, epoch, tid);
 }
 
 // ---- v3: TMA-fed streaming GEMV for bandwidth-bound shapes.
@@ -880,7 +866,6 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
     // stage the activation vector (consumer warps + epilogue warp; barrier 1 is theirs)
     {
         const float *xsrc = p.emb ? p.emb + (size_t)p.ctl[CTL_TOKEN] * p.n : p.x_in;
-        if (p.ll_in) tp_reduce_into_x(p, 1, PRO_THREADS);  // tensor parallel: x += sum of all ranks' partial rows
         if (tid == 0) {
             const uint32_t bytes = (uint32_t)p.n * 4u;
             mbar_expect_tx(&xbar, bytes);
@@ -998,6 +983,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) gemv_tma_kernel(const GemvPara
             }
             if (lane == 0 && best) atomicMax(p.amax, best);
         }
+        if (EPI == EPI_XCHG && p.xres) tp_reduce_tail(p, epoch, lane);
         if (lane == 0) L2B_STAMP(p.trace, 7);
         return;
     }

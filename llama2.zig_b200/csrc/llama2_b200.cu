@@ -138,10 +138,9 @@ struct l2b_ctx {
     //   ll_red    [2L reduce points][world source ranks][dim] LL units   (wo / w2 partial rows)
     //   ll_logits [vocab] LL units                                       (classifier slices of all ranks)
     //   ll_amax   [world][2] LL units                                    (packed argmax keys)
-    //   rdone     [2L][dim/128] slice flags (local use only)
     bool use_p2p = false;
     unsigned char *arena = nullptr;
-    size_t arena_bytes = 0, off_red = 0, off_logits = 0, off_amax = 0, off_rdone = 0;
+    size_t arena_bytes = 0, off_red = 0, off_logits = 0, off_amax = 0;
     unsigned char *peer_arena[MAX_TP] = {};
     std::vector<void *> ipc_opened;
     unsigned long long spin_ns = 20ull * 1000000000ull;   // bound on every peer wait (L2B_SPIN_TIMEOUT_MS)
@@ -664,10 +663,7 @@ unsigned long long *ll_logits_at(unsigned char *arena, const l2b_ctx *c) {
 unsigned long long *ll_amax_at(unsigned char *arena, const l2b_ctx *c, int src_rank) {
     return reinterpret_cast<unsigned long long *>(arena + c->off_amax) + 2 * (size_t)src_rank;
 }
-int tp_slices(const l2b_ctx *c) { return (c->dim / 4 + TP_SLICE4 - 1) / TP_SLICE4; }
-unsigned int *rdone_at(const l2b_ctx *c, int slot) {
-    return reinterpret_cast<unsigned int *>(c->arena + c->off_rdone) + (size_t)slot * tp_slices(c);
-}
+
 
 int launch_small(l2b_ctx *ctx, const void *fn, dim3 grid, dim3 block, void **args, cudaStream_t st, bool pdl) {
     cudaLaunchConfig_t lc{};
@@ -707,14 +703,13 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, StepMode mode) {
     const int dim = ctx->dim;
     const bool tp = ctx->world > 1;
     const bool p2p = tp && ctx->use_p2p;
-    auto consume_slot = [&](GemvParams &g, int slot) {      // x += sum of all ranks' partial rows of `slot`
-        g.ll_in = ll_red_at(ctx->arena, ctx, slot, 0);
-        g.rdone = rdone_at(ctx, slot);
-        g.xworld = ctx->world;
-    };
-    auto produce_slot = [&](GemvParams &g, int slot) {      // my partial rows go to every rank
+    // my partial rows go to every rank; slice owners then fold all ranks' rows into x (tp_reduce_tail)
+    auto produce_slot = [&](GemvParams &g, int slot, float *x) {
         g.ll_ndst = ctx->world;
         for (int r = 0; r < ctx->world; ++r) g.ll_out[r] = ll_red_at(ctx->peer_arena[r], ctx, slot, ctx->rank);
+        g.ll_in = ll_red_at(ctx->arena, ctx, slot, 0);
+        g.xres = x;
+        g.xworld = ctx->world;
     };
     // wo / w2: row-parallel GEMV whose result is added to the residual stream (:392-395, :419-422)
     auto residual_gemv = [&](GemvParams &g, float *x, int slot, const char *name, int l) -> int {
@@ -724,7 +719,7 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, StepMode mode) {
             g.out0 = x;
             rc = launch_gemv(ctx, EPI_RESID, g, st, name, l);
         } else if (p2p) {
-            produce_slot(g, slot);
+            produce_slot(g, slot, x);
             rc = launch_gemv(ctx, EPI_XCHG, g, st, name, l);
         } else {
             g.out0 = ctx->delta;
@@ -761,8 +756,6 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, StepMode mode) {
             p.emb = ctx->emb;                 // :295-296
             p.x_out = Xc;
             p.bump_epoch = 1;
-        } else if (p2p) {
-            consume_slot(p, 2 * (l - 1) + 1); // pending :422 of the previous layer
         }
         p.gamma = ctx->rms_att + (size_t)l * dim;
         p.w0 = ctx->wq + (size_t)l * ctx->q_loc * dim;
@@ -803,7 +796,6 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, StepMode mode) {
         f.ctl = ctx->ctl;
         f.n = dim;
         fold_pending(f);
-        if (p2p) consume_slot(f, 2 * l);
         f.gamma = ctx->rms_ffn + (size_t)l * dim;
         if (ctx->fuse_ffn && l + 1 < c.n_layers) {
             // ---- ... + w2 in the same launch (:419); the last layer stays unfused so that the
@@ -840,7 +832,6 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, StepMode mode) {
     k.n = dim;
     fold_pending(k);
     ctx->final_X = Xc;
-    if (p2p) consume_slot(k, 2 * (c.n_layers - 1) + 1);
     k.gamma = ctx->rms_final;
     k.w0 = ctx->wcls;
     k.total_rows = ctx->vocab_loc; k.rows0 = ctx->vocab_loc;
@@ -1172,8 +1163,6 @@ int create_rank(l2b_ctx *ctx, const l2b_config *cfg, const Source &src, const fl
         ctx->off_red = o;    o += slots * world * dim * sizeof(unsigned long long);
         ctx->off_logits = o; o += (size_t)V * sizeof(unsigned long long);
         ctx->off_amax = o;   o += (size_t)world * 2 * sizeof(unsigned long long);
-        o = (o + 255) & ~(size_t)255;
-        ctx->off_rdone = o;  o += slots * (size_t)tp_slices(ctx) * sizeof(unsigned int);
         ctx->arena_bytes = (o + 255) & ~(size_t)255;
         L2B_TRY(dev_alloc(ctx, &ctx->arena, ctx->arena_bytes));
         L2B_TRY(cuda_try(ctx, cudaMemsetAsync(ctx->arena, 0, ctx->arena_bytes, ctx->stream), "memset"));
