@@ -414,6 +414,17 @@ def run_workload(workload, args, rank, world, dist, sync, flush, clock_index):
     }
     if world > 1 and forced is not None:
         out["parity"] = tp_parity(t, ck, workload, rank, device)
+    if world == 1 and forced is not None:
+        # prompt prefill: the same positions as one prompt, on the device, no logits
+        t.reset()
+        t.prefill(np.concatenate([[1], forced[:positions - 1]]).astype(np.int32), 0, want_logits=False)
+        t.reset()
+        flush()
+        t.prefill(np.concatenate([[1], forced[:positions - 1]]).astype(np.int32), 0, want_logits=False)
+        pms, _ = t.last_timing()
+        out["prefill"] = {"tokens": positions, "tokens_per_s": positions / (pms * 1e-3), "device_ms": pms,
+                          "note": "l2b_prefill: prompt positions on the device, classifier skipped; "
+                                  "4 positions per weight pass on bandwidth-bound shapes"}
     t.close()
     return out
 
@@ -465,7 +476,7 @@ def main():
             if w != workload:
                 r = run_workload(w, args, rank, world, dist, sync, flush, clock_index)
                 also[w] = {k: r[k] for k in ("value", "ms_per_step", "device_ms_per_step", "e2e", "roofline",
-                                             "whole_step", "kernels", "positions", "data")}
+                                             "whole_step", "kernels", "positions", "data", "prefill") if k in r}
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -490,6 +501,8 @@ def main():
         }
         if main_res.get("parity") is not None:
             line["parity"] = main_res["parity"]
+        if main_res.get("prefill") is not None:
+            line["prefill"] = main_res["prefill"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -1082,6 +1082,9 @@ struct AttnParams {
     unsigned int *counters;  // (n_heads), zero between launches
     int head_size, kv_dim, kv_mul, nsplit, min_chunk;
     unsigned long long *trace;
+    // batched prompt prefill: gridDim.z positions at once; query z sits at position pos_base + z and
+    // uses q / xb / partial buffers offset by z (pos_base < 0: single position from the control block)
+    int pos_base, q_stride;
 };
 
 __device__ __forceinline__ int attn_lanes_per_row(int hs4) {
@@ -1244,15 +1247,20 @@ __global__ void __launch_bounds__(NT) attention_flash_kernel(const AttnParams p)
     if (threadIdx.x == 0) L2B_STAMP(atr, 2);
     if (p.ctl[CTL_DONE]) return;
 
-    const int h = blockIdx.x, s = blockIdx.y;
+    const int h = blockIdx.x, s = blockIdx.y, z = blockIdx.z;
     const int hs = p.head_size, hs4 = hs >> 2;
-    const int T = p.ctl[CTL_POS] + 1;
+    const int T = (p.pos_base >= 0 ? p.pos_base + z : p.ctl[CTL_POS]) + 1;
     int chunk = (T + p.nsplit - 1) / p.nsplit;
     if (chunk < p.min_chunk) chunk = p.min_chunk;
     const int active = (T + chunk - 1) / chunk;
     if (s >= active) return;
     const int t0 = s * chunk;
     const int t1 = min(T, t0 + chunk);
+    const float *qz = p.q + (size_t)z * p.q_stride;
+    float *xbz = p.xb + (size_t)z * p.q_stride;
+    float *part_o_z = p.part_o + (size_t)z * gridDim.x * p.nsplit * hs;
+    float *part_ml_z = p.part_ml + (size_t)z * gridDim.x * p.nsplit * 2;
+    unsigned int *counters_z = p.counters + (size_t)z * gridDim.x;
 
     const int LPR = hs4 / NF;                 // lanes per row (8, 4, 2 or 1)
     const int RPW = 32 / LPR;                 // rows per warp pass
@@ -1265,7 +1273,7 @@ __global__ void __launch_bounds__(NT) attention_flash_kernel(const AttnParams p)
     float *wgt = mlp + 2 * NG;                                // [NG]
 
     const size_t hoff = (size_t)(h / p.kv_mul) * hs;          // :369, :382
-    const float4 *q4 = reinterpret_cast<const float4 *>(p.q + (size_t)h * hs);
+    const float4 *q4 = reinterpret_cast<const float4 *>(qz + (size_t)h * hs);
     const float *kb = p.kcache + hoff, *vb = p.vcache + hoff;
     const float root_hs = sqrtf((float)hs);
 
@@ -1346,37 +1354,37 @@ __global__ void __launch_bounds__(NT) attention_flash_kernel(const AttnParams p)
         for (int g = 0; g < NG; ++g) o = fmaf(wgt[g], accp[(size_t)g * hs + tid], o);
 
     if (active == 1) {
-        if (tid < hs) p.xb[(size_t)h * hs + tid] = o / L;
+        if (tid < hs) xbz[(size_t)h * hs + tid] = o / L;
         if (tid == 0) L2B_STAMP(atr, 7);
         return;
     }
 
     // ---- several timeline splits: publish (M, L, unnormalised out), last arriver merges
-    if (tid < hs) p.part_o[((size_t)h * p.nsplit + s) * hs + tid] = o;
+    if (tid < hs) part_o_z[((size_t)h * p.nsplit + s) * hs + tid] = o;
     if (tid == 0) {
-        p.part_ml[((size_t)h * p.nsplit + s) * 2 + 0] = M;
-        p.part_ml[((size_t)h * p.nsplit + s) * 2 + 1] = L;
+        part_ml_z[((size_t)h * p.nsplit + s) * 2 + 0] = M;
+        part_ml_z[((size_t)h * p.nsplit + s) * 2 + 1] = L;
     }
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        const unsigned int prev = atomicAdd(&p.counters[h], 1u);
+        const unsigned int prev = atomicAdd(&counters_z[h], 1u);
         is_last = (prev == (unsigned int)(active - 1));
     }
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    if (tid == 0) p.counters[h] = 0u;  // ready for the next launch
-    const volatile float *ml = p.part_ml + (size_t)h * p.nsplit * 2;
+    if (tid == 0) counters_z[h] = 0u;  // ready for the next launch
+    const volatile float *ml = part_ml_z + (size_t)h * p.nsplit * 2;
     float MM = -INFINITY;
     for (int j = 0; j < active; ++j) MM = fmaxf(MM, ml[j * 2]);
     float Lsum = 0.0f;
     for (int j = 0; j < active; ++j) Lsum += expf(ml[j * 2] - MM) * ml[j * 2 + 1];
     if (tid < hs) {
-        const volatile float *pb = p.part_o + (size_t)h * p.nsplit * hs;
+        const volatile float *pb = part_o_z + (size_t)h * p.nsplit * hs;
         float a2 = 0.0f;
         for (int j = 0; j < active; ++j) a2 = fmaf(expf(ml[j * 2] - MM), pb[(size_t)j * hs + tid], a2);
-        p.xb[(size_t)h * hs + tid] = a2 / Lsum;
+        xbz[(size_t)h * hs + tid] = a2 / Lsum;
     }
 }
 

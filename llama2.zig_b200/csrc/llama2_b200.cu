@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "l2b_device.cuh"
+#include "l2b_prefill.cuh"
 
 using namespace l2b;
 
@@ -106,6 +107,12 @@ struct l2b_ctx {
     float *final_X = nullptr;                // which of the two holds x after a step
     float *attn_parts = nullptr, *ffn_parts = nullptr;   // small-model fusion: (n_heads, dim) and (hidden/32, dim) partial vectors
     bool fuse_attn = false, fuse_ffn = false;
+    // batched prompt prefill (l2b_prefill, bandwidth-bound shapes): PF_MAXB positions per weight pass
+    float *pf_x = nullptr, *pf_q = nullptr, *pf_xb = nullptr, *pf_hb = nullptr;   // [PF_MAXB][dim | q | q | hidden]
+    float *pf_part_o = nullptr, *pf_part_ml = nullptr;
+    unsigned int *pf_counters = nullptr;
+    int *pf_tokens = nullptr;
+    bool pf_ready = false, pf_ok = false;
     int attn_R = 1;                          // CTAs per head cluster of attn_wo_kernel
     float *delta = nullptr;                  // L2B_TP=nccl baseline only: partial rows before the NCCL all-reduce
     float *q = nullptr, *xb = nullptr, *hb = nullptr, *logits = nullptr, *logits_loc = nullptr;
@@ -637,6 +644,7 @@ int launch_attention(l2b_ctx *ctx, int layer, cudaStream_t st) {
     a.kv_mul = ctx->kv_mul;
     a.nsplit = ctx->nsplit;
     a.min_chunk = ctx->min_chunk;
+    a.pos_base = -1;
     a.trace = trace_slot(ctx);
     size_t smem = ctx->attn_smem;
     attn_fn fn = pick_attention(ctx->head_size, ctx->attn_flash, &smem);
@@ -1581,6 +1589,176 @@ int32_t l2b_forward_sample(l2b_ctx *ctx, int32_t token, int32_t pos, float tempe
     return L2B_OK;
 }
 
+}  // extern "C" (templates below)
+
+// ---- batched prompt prefill (csrc/l2b_prefill.cuh) --------------------------------------------
+typedef void (*pf_fn)(const PrefillParams);
+template <int NB>
+pf_fn pf_pick(int epi) {
+    switch (epi) {
+    case EPI_QKV: return prefill_gemm_kernel<EPI_QKV, NB>;
+    case EPI_SILU: return prefill_gemm_kernel<EPI_SILU, NB>;
+    default: return prefill_gemm_kernel<EPI_RESID, NB>;
+    }
+}
+constexpr size_t kPfSmemBudget = 227 * 1024 - 8192;   // the prefill kernels keep ~6.5 KB of static shared memory
+
+// can this context prefill PF_MAXB positions per weight pass?  Single GPU, flash attention, and all
+// four per-layer GEMVs bandwidth-bound shapes of the TMA-ring kernel; otherwise l2b_prefill runs the
+// positions one by one on the device (same results, weights streamed once per position).
+static int pf_prepare(l2b_ctx *ctx) {
+    if (ctx->pf_ready) return L2B_OK;
+    ctx->pf_ready = true;
+    const char *env = getenv("L2B_PREFILL_BATCH");
+    if (env && env[0] == '0') return L2B_OK;
+    const uint64_t dim = ctx->dim, hid = ctx->hid_loc, q = ctx->q_loc;
+    size_t smem = 0;
+    const bool shapes_ok = ctx->world == 1 && !ctx->leader && dim >= (uint64_t)ctx->big_min_n && hid >= (uint64_t)ctx->big_min_n &&
+                           dim <= 5 * (TMA_THREADS - 32) * 4 && ctx->gemv8_min_bytes >= 0 &&
+                           dim * dim * 4 >= (uint64_t)ctx->gemv8_min_bytes && ctx->attn_flash &&
+                           pick_attention(ctx->head_size, true, &smem) != attention_kernel &&
+                           (kPfSmemBudget - PF_MAXB * dim * 4) / ((size_t)TMA_STAGE_FLOATS * 4) >= 2 &&
+                           (kPfSmemBudget - 2 * hid * 4) / ((size_t)TMA_STAGE_FLOATS * 4) >= 2;
+    if (!shapes_ok) return L2B_OK;
+    L2B_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->pf_x, PF_MAXB * dim))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->pf_q, PF_MAXB * q))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->pf_xb, PF_MAXB * q))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->pf_hb, PF_MAXB * hid))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->pf_part_o, (size_t)PF_MAXB * ctx->heads_loc * ctx->nsplit * ctx->head_size))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->pf_part_ml, (size_t)PF_MAXB * ctx->heads_loc * ctx->nsplit * 2))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->pf_counters, (size_t)PF_MAXB * ctx->heads_loc))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->pf_tokens, (size_t)ctx->cfg.seq_len))) return rc;
+    L2B_CUDA(ctx, cudaMemsetAsync(ctx->pf_counters, 0, (size_t)PF_MAXB * ctx->heads_loc * sizeof(unsigned int), ctx->stream));
+    for (int epi : {(int)EPI_QKV, (int)EPI_SILU, (int)EPI_RESID}) {
+        L2B_CUDA(ctx, cudaFuncSetAttribute(pf_pick<PF_MAXB>(epi), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPfSmemBudget));
+        L2B_CUDA(ctx, cudaFuncSetAttribute(pf_pick<2>(epi), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPfSmemBudget));
+    }
+    ctx->pf_ok = true;
+    return L2B_OK;
+}
+
+template <int NB>
+static int pf_launch(l2b_ctx *ctx, int epi, PrefillParams p, cudaStream_t st) {
+    const size_t xbytes = (size_t)NB * p.n * 4;
+    int nstage = (int)((kPfSmemBudget - xbytes) / ((size_t)TMA_STAGE_FLOATS * 4));
+    if (nstage > TMA_MAX_STAGES) nstage = TMA_MAX_STAGES;
+    p.nstage = nstage;
+    int grid = ctx->num_sms;
+    const int npairs = (p.total_rows + 1) / 2;
+    if (grid > npairs) grid = npairs;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(TMA_THREADS);
+    lc.dynamicSmemBytes = (size_t)nstage * TMA_STAGE_FLOATS * 4 + xbytes;
+    lc.stream = st;
+    cudaLaunchAttribute at[1] = {pdl_attr()};
+    lc.attrs = at;
+    lc.numAttrs = ctx->use_pdl ? 1 : 0;
+    L2B_CUDA(ctx, cudaLaunchKernelEx(&lc, pf_pick<NB>(epi), p));
+    ++ctx->last_launches;
+    return L2B_OK;
+}
+
+// n_tokens positions starting at pos0, PF_MAXB per pass over the weights; KV cache filled, no logits
+static int prefill_batched(l2b_ctx *ctx, const int32_t *tokens, int n_tokens, int pos0) {
+    const l2b_config &c = ctx->cfg;
+    const int dim = ctx->dim;
+    cudaStream_t st = ctx->stream;
+    L2B_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < n_tokens; ++i) ctx->h_gen[i] = tokens[i];
+    L2B_CUDA(ctx, cudaMemcpyAsync(ctx->pf_tokens, ctx->h_gen, (size_t)n_tokens * sizeof(int), cudaMemcpyHostToDevice, st));
+    fill_ctl(ctx, tokens[0], pos0, 0, 1.0f, -1.0f);          // DONE = 0 for the attention kernel
+    L2B_CUDA(ctx, cudaMemcpyAsync(ctx->ctl, ctx->h_ctl, CTL_HOST_WORDS * sizeof(int), cudaMemcpyHostToDevice, st));
+    L2B_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    ctx->last_launches = 0;
+    size_t attn_smem = 0;
+    attn_fn afn = pick_attention(ctx->head_size, true, &attn_smem);
+    for (int done = 0; done < n_tokens; done += PF_MAXB) {
+        const int nb = n_tokens - done < PF_MAXB ? n_tokens - done : PF_MAXB;
+        const int pos = pos0 + done;
+        for (int l = 0; l < c.n_layers; ++l) {
+            // ---- rmsnorm + q,k,v + RoPE + KV append for nb positions (:305-358)
+            PrefillParams p{};
+            p.n = dim; p.nb = nb; p.pos0 = pos;
+            p.x_in = ctx->pf_x;
+            if (l == 0) { p.emb = ctx->emb; p.tokens = ctx->pf_tokens + done; p.x_out = ctx->pf_x; }
+            p.gamma = ctx->rms_att + (size_t)l * dim;
+            p.w0 = ctx->wq + (size_t)l * ctx->q_loc * dim;
+            p.w1 = ctx->wk + (size_t)l * ctx->kv_loc * dim;
+            p.w2 = ctx->wv + (size_t)l * ctx->kv_loc * dim;
+            p.rows0 = ctx->q_loc; p.rows1 = ctx->kv_loc; p.rows2 = ctx->kv_loc;
+            p.total_rows = ctx->q_loc + 2 * ctx->kv_loc;
+            p.out0 = ctx->pf_q;
+            const size_t loff = (size_t)l * c.seq_len * ctx->kv_loc;
+            p.kcache = ctx->kcache + loff;
+            p.vcache = ctx->vcache + loff;
+            p.rope_cos = ctx->rope_cos; p.rope_sin = ctx->rope_sin;
+            p.head_size = ctx->head_size; p.kv_dim = ctx->kv_loc;
+            int rc = pf_launch<PF_MAXB>(ctx, EPI_QKV, p, st);
+            if (rc) return rc;
+            // ---- attention of the nb queries (:361-389); query z sees positions 0 .. pos+z
+            AttnParams a{};
+            a.ctl = ctx->ctl; a.q = ctx->pf_q; a.kcache = ctx->kcache + loff; a.vcache = ctx->vcache + loff;
+            a.xb = ctx->pf_xb; a.part_o = ctx->pf_part_o; a.part_ml = ctx->pf_part_ml; a.counters = ctx->pf_counters;
+            a.head_size = ctx->head_size; a.kv_dim = ctx->kv_loc; a.kv_mul = ctx->kv_mul;
+            a.nsplit = ctx->nsplit; a.min_chunk = ctx->min_chunk;
+            a.pos_base = pos; a.q_stride = ctx->q_loc;
+            cudaLaunchConfig_t lc{};
+            lc.gridDim = dim3(ctx->heads_loc, ctx->nsplit, nb);
+            lc.blockDim = dim3(NT);
+            lc.dynamicSmemBytes = attn_smem;
+            lc.stream = st;
+            cudaLaunchAttribute at[1] = {pdl_attr()};
+            lc.attrs = at;
+            lc.numAttrs = ctx->use_pdl ? 1 : 0;
+            L2B_CUDA(ctx, cudaLaunchKernelEx(&lc, afn, a));
+            ++ctx->last_launches;
+            // ---- wo + residual (:392-395)
+            PrefillParams o{};
+            o.n = ctx->q_loc; o.nb = nb; o.pos0 = pos;
+            o.x_in = ctx->pf_xb;
+            o.w0 = ctx->wo + (size_t)l * dim * ctx->q_loc;
+            o.total_rows = dim; o.rows0 = dim;
+            o.out0 = ctx->pf_x;
+            rc = pf_launch<PF_MAXB>(ctx, EPI_RESID, o, st);
+            if (rc) return rc;
+            // ---- rmsnorm + w1,w3 + SiLU*mul (:398-416)
+            PrefillParams f{};
+            f.n = dim; f.nb = nb; f.pos0 = pos;
+            f.x_in = ctx->pf_x;
+            f.gamma = ctx->rms_ffn + (size_t)l * dim;
+            f.w0 = ctx->w1 + (size_t)l * ctx->hid_loc * dim;
+            f.w1 = ctx->w3 + (size_t)l * ctx->hid_loc * dim;
+            f.rows0 = ctx->hid_loc;
+            f.total_rows = 2 * ctx->hid_loc;
+            f.out0 = ctx->pf_hb;
+            rc = pf_launch<PF_MAXB>(ctx, EPI_SILU, f, st);
+            if (rc) return rc;
+            // ---- w2 + residual (:419-422); hidden-sized inputs: two positions per pass (shared memory)
+            for (int b = 0; b < nb; b += 2) {
+                PrefillParams d{};
+                d.n = ctx->hid_loc; d.nb = nb - b < 2 ? nb - b : 2; d.pos0 = pos + b;
+                d.x_in = ctx->pf_hb + (size_t)b * ctx->hid_loc;
+                d.w0 = ctx->w2 + (size_t)l * dim * ctx->hid_loc;
+                d.total_rows = dim; d.rows0 = dim;
+                d.out0 = ctx->pf_x + (size_t)b * dim;
+                rc = pf_launch<2>(ctx, EPI_RESID, d, st);
+                if (rc) return rc;
+            }
+        }
+    }
+    L2B_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    L2B_CUDA(ctx, cudaStreamSynchronize(st));
+    L2B_CUDA(ctx, cudaGetLastError());
+    L2B_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    if (pos0 + n_tokens > ctx->n_appended) ctx->n_appended = pos0 + n_tokens;
+    return L2B_OK;
+}
+
+extern "C" {
+
 // n_steps replays of a device-loop graph (G_ARGMAX_LOOP or G_PREFILL_LOOP) starting at (token, pos)
 static int run_device_loop(l2b_ctx *ctx, int which, int token, int pos, int n_steps, const int32_t *forced,
                            int stop_on_bos, int *done_out) {
@@ -1655,9 +1833,9 @@ int32_t l2b_generate_argmax(l2b_ctx *ctx, int32_t token, int32_t pos, int32_t n_
 // Prompt prefill (src/main.zig:996-1000 feeds prompt tokens through transformer() one
 // at a time and throws their logits away).  All positions run back to back on the device with
 // the next token forced, the classifier (60 % of stories15M's bytes) is skipped for every position
-// whose logits nobody reads, and no position pays a host round trip; the arithmetic per position
-// is the decode step's own, so the KV cache and any later logits are bit-identical to n calls of
-// l2b_forward.
+// whose logits nobody reads, and no position pays a host round trip.  On bandwidth-bound shapes
+// (llama2-7B on one GPU) PF_MAXB = 4 positions additionally share each pass over the weights
+// (csrc/l2b_prefill.cuh).  Per (row, position) the arithmetic is the decode step's own.
 int32_t l2b_prefill(l2b_ctx *ctx, const int32_t *tokens, int32_t n_tokens, int32_t pos0, float *host_logits) {
     if (!ctx || !tokens || n_tokens <= 0) return fail(ctx, L2B_ERR_INVALID_ARG, "bad prefill arguments");
     int rc = check_step_args(ctx, tokens[0], pos0);
@@ -1666,7 +1844,13 @@ int32_t l2b_prefill(l2b_ctx *ctx, const int32_t *tokens, int32_t n_tokens, int32
     for (int i = 0; i < n_tokens; ++i)
         if (tokens[i] < 0 || tokens[i] >= ctx->cfg.vocab_size) return fail(ctx, L2B_ERR_INVALID_ARG, "token out of range");
     const int n_silent = host_logits ? n_tokens - 1 : n_tokens;   // positions whose logits are dropped
-    if (n_silent > 0) {
+    rc = pf_prepare(ctx);
+    if (rc) return rc;
+    if (n_silent > 0 && ctx->pf_ok) {
+        // bandwidth-bound shapes: PF_MAXB positions share each pass over the weights
+        rc = prefill_batched(ctx, tokens, n_silent, pos0);
+        if (rc) return rc;
+    } else if (n_silent > 0) {
         std::vector<int32_t> forced(n_silent);
         for (int i = 0; i < n_silent; ++i) forced[i] = tokens[i + 1 < n_tokens ? i + 1 : i];
         int done = 0;
@@ -1959,6 +2143,7 @@ int32_t l2b_op_attention_head(int32_t device, float *out, const float *q, const 
     a.ctl = ctl; a.q = dq; a.kcache = dk; a.vcache = dv; a.xb = dout; a.part_o = po; a.part_ml = pml;
     a.counters = cnt; a.head_size = head_size; a.kv_dim = kv_stride; a.kv_mul = 1; a.nsplit = nsplit;
     a.min_chunk = 64;
+    a.pos_base = -1;
     int cap = (n_pos + nsplit - 1) / nsplit;
     if (cap < 64) cap = 64;
     const int G = NT / (head_size / 4);

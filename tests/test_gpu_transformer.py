@@ -341,3 +341,30 @@ def test_prefill_equals_token_by_token(l2b, oracle, stories15m):
         assert nxt_a == nxt_b == gold[41]
         with pytest.raises(l2b.L2BError):
             b.prefill([1] * 300, 0)               # runs past seq_len
+
+
+def test_batched_prefill_on_bandwidth_bound_shapes(l2b, oracle):
+    """SURVEY 8f.2 on llama2-7B shapes (2 layers): l2b_prefill runs 4 prompt positions per pass over
+    the weights (csrc/l2b_prefill.cuh).  KV cache and the next logits must equal the token-by-token
+    path (same per-row summation order => expected bit-identical; bar 1e-6) and the oracle (1e-4)."""
+    ck, om = make_pair(l2b, oracle, (4096, 11008, 2, 32, 32, -32000, 2048), 7)
+    toks = teacher_tokens(12, ck.vocab_size)           # 11 silent positions = 2 full chunks + 3, then 1 with logits
+    with l2b.Transformer(ck) as a, l2b.Transformer(ck) as b:
+        for pos, tok in enumerate(toks):
+            want = a.forward(tok, pos)
+            ref = om.forward(tok, pos)
+        got = b.prefill(toks, 0)
+        ms, launches = b.last_timing()
+        assert rel_err(got, ref) <= REL_TOL
+        assert rel_err(got, want) <= 1e-6
+        kv_a, kv_b = a.state("key_cache"), b.state("key_cache")
+        va, vb = a.state("value_cache"), b.state("value_cache")
+        S, kvd = 2048, 4096
+        for l in range(2):
+            sl = slice(l * S * kvd, l * S * kvd + 12 * kvd)
+            assert np.max(np.abs(kv_a[sl] - kv_b[sl])) <= 1e-6 * np.max(np.abs(kv_a[sl]))
+            assert np.max(np.abs(va[sl] - vb[sl])) <= 1e-6 * np.max(np.abs(va[sl]))
+        print("batched prefill bit-identical to token-by-token:", bool(np.array_equal(got, want) and np.array_equal(kv_a[:12 * kvd], kv_b[:12 * kvd])))
+        # decoding continues from the prefilled cache
+        nxt = teacher_tokens(13, ck.vocab_size)[12]
+        assert rel_err(b.forward(nxt, 12), a.forward(nxt, 12)) <= 1e-6
