@@ -317,16 +317,41 @@ __device__ __forceinline__ void tp_reduce_tail(const GemvParams &p, unsigned int
         const int i = s * TP_SLICE4 + lane;
         if (i < n4) {
             float4 v = __ldcg(x4 + i);
-            for (int r = 0; r < p.xworld; ++r) {
-                const unsigned long long *u = p.ll_in + (size_t)r * p.total_rows + (size_t)i * 4;
-                uint4 a = ll_load2(u), b = ll_load2(u + 2);
-                while (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch) {
-                    if (sg.expired()) break;
-                    a = ll_load2(u);
-                    b = ll_load2(u + 2);
+            // the units of up to four ranks are requested together (measured r02, 8 GPUs: polling rank
+            // after rank serialised eight L2 round trips and made this tail 6 us), then re-polled
+            // until every flag carries this step's epoch; the sum itself stays in rank order
+            for (int rb = 0; rb < p.xworld; rb += 4) {
+                uint4 a[4], b[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    a[k] = b[k] = make_uint4(0u, epoch, 0u, epoch);        // ranks beyond the world count as "arrived"
+                    if (rb + k < p.xworld) {
+                        const unsigned long long *u = p.ll_in + (size_t)(rb + k) * p.total_rows + (size_t)i * 4;
+                        a[k] = ll_load2(u);
+                        b[k] = ll_load2(u + 2);
+                    }
                 }
-                v.x += __uint_as_float(a.x); v.y += __uint_as_float(a.z);   // accum(), :708-713
-                v.z += __uint_as_float(b.x); v.w += __uint_as_float(b.z);
+                bool all = false;
+                while (!all) {
+                    all = true;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (a[k].y != epoch || a[k].w != epoch || b[k].y != epoch || b[k].w != epoch) {
+                            const unsigned long long *u = p.ll_in + (size_t)(rb + k) * p.total_rows + (size_t)i * 4;
+                            a[k] = ll_load2(u);
+                            b[k] = ll_load2(u + 2);
+                            all = false;
+                        }
+                    }
+                    if (!all && sg.expired()) break;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (rb + k < p.xworld) {
+                        v.x += __uint_as_float(a[k].x); v.y += __uint_as_float(a[k].z);   // accum(), :708-713
+                        v.z += __uint_as_float(b[k].x); v.w += __uint_as_float(b[k].z);
+                    }
+                }
             }
             __stcg(x4 + i, v);
         }

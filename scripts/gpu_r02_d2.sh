@@ -5,7 +5,7 @@ OUT=gpurun_out; mkdir -p $OUT
 timeout 1500 python -m pytest tests -m gpu -q --timeout 600 --timeout-method=thread -p no:cacheprovider \
     --deselect tests/test_gpu_tp.py > $OUT/r02d_pytest.log 2>&1
 echo "pytest rc=$?" >> $OUT/r02d_pytest.log; tail -8 $OUT/r02d_pytest.log
-for PF in 0 1 2 3; do
+for PF in 0 2; do
   L2B_TMA_PREFILL=$PF timeout 300 python bench.py --steps 3 --warmup 3 --also none --no-cpu-baseline > $OUT/r02d_bench_7b_pf$PF.json 2> $OUT/r02d_bench_7b_pf$PF.err
   python - <<PY
 import json
