@@ -533,6 +533,7 @@ __global__ void __launch_bounds__(NT) gemv_kernel(const GemvParams p) {
             }
         }
     };
+    if (tid == 0) L2B_STAMP(p.trace, 0);
     if (tile < ntiles) issue(tile, 0);
     if (tid == 0) {
         mbar_init(&bar, 1);
@@ -548,7 +549,9 @@ __global__ void __launch_bounds__(NT) gemv_kernel(const GemvParams p) {
     pdl_wait();
     if (p.ctl[CTL_DONE]) return;  // generation loop already ended (BOS)
     if (p.bump_epoch && blockIdx.x == 0 && tid == 0) const_cast<int *>(p.ctl)[CTL_EPOCH] += 1;
+    if (tid == 0) L2B_STAMP(p.trace, 2);
     gemv_stage_input(p, xs, aux, &bar, scratch);
+    if (tid == 0) L2B_STAMP(p.trace, 3);
 
     const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
     const int pos = p.ctl[CTL_POS];
@@ -621,7 +624,9 @@ __global__ void __launch_bounds__(NT) gemv_kernel(const GemvParams p) {
     }
     if (!triggered) pdl_launch_dependents();
     gemv_finish_argmax<EPI>(p, best, &blk_key);
+    if (tid == 0) L2B_STAMP(p.trace, 5);
     if (EPI == EPI_XCHG && p.xres && tid < 32) tp_reduce_tail(p, epoch, tid);
+    if (tid == 0) L2B_STAMP(p.trace, 7);
 }
 
 // ---- v2: bandwidth-bound shapes (n >= 1024, many MB).  The whole CTA (256 threads) walks the

@@ -1074,15 +1074,16 @@ int create_rank(l2b_ctx *ctx, const l2b_config *cfg, const Source &src, const fl
     L2B_TRY(dev_alloc(ctx, &ctx->X, dim));
     L2B_TRY(dev_alloc(ctx, &ctx->Xalt, dim));
     {
-        // small-model fusion (measured on B200, profiles/r02_small_models.md): a step of stories15M is 31
-        // kernels of ~3 us; attention+wo as one cluster kernel and the FFN as one kernel make it 20
+        // small-model fusion (measured on B200, profiles/r02_small_models.md): attention + wo as one
+        // cluster kernel (8 CTAs per head) is +7 % on stories15M (31 -> 25 kernels per token) and -1 % on
+        // stories110M, so it is on for dim <= 512 only; the fused FFN kernel is slower everywhere (off)
         const char *ef = getenv("L2B_FUSE");
-        const int want = ef ? atoi(ef) : 3;                       // bit 0: attention+wo, bit 1: FFN
+        const int want = ef ? atoi(ef) : (dim <= 512 ? 1 : 0);     // bit 0: attention+wo, bit 1: FFN
         size_t smem_aw = 0;
         ctx->fuse_attn = (want & 1) && world == 1 && dim < 1024 && pick_attn_wo((int)hs, &smem_aw) != nullptr;
         ctx->fuse_ffn = (want & 2) && world == 1 && dim <= 8 * FFN_MAXU * 4 && hid % FFN_HSZ == 0;
         const char *er = getenv("L2B_ATTN_R");
-        ctx->attn_R = er && atoi(er) >= 1 && atoi(er) <= 8 ? atoi(er) : 4;
+        ctx->attn_R = er && atoi(er) >= 1 && atoi(er) <= 8 ? atoi(er) : 8;
         if (ctx->fuse_attn) L2B_TRY(dev_alloc(ctx, &ctx->attn_parts, (size_t)cfg->n_heads * dim));
         if (ctx->fuse_ffn) L2B_TRY(dev_alloc(ctx, &ctx->ffn_parts, (size_t)(hid / FFN_HSZ) * dim));
     }
