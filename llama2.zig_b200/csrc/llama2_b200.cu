@@ -20,6 +20,7 @@
 #include <string>
 #include <vector>
 
+#include "l2b_cluster.cuh"
 #include "l2b_device.cuh"
 #include "l2b_prefill.cuh"
 
@@ -114,6 +115,11 @@ struct l2b_ctx {
     int *pf_tokens = nullptr;
     bool pf_ready = false, pf_ok = false;
     int attn_R = 1;                          // CTAs per head cluster of attn_wo_kernel
+    // small models: all layers of a step in one cluster kernel (csrc/l2b_cluster.cuh)
+    bool use_cluster = false;
+    int cluster_C = 16;
+    void (*cluster_fn)(const ClusterParams) = nullptr;
+    size_t cluster_smem = 0;
     float *delta = nullptr;                  // L2B_TP=nccl baseline only: partial rows before the NCCL all-reduce
     float *q = nullptr, *xb = nullptr, *hb = nullptr, *logits = nullptr, *logits_loc = nullptr;
     float *kcache = nullptr, *vcache = nullptr;     // (L, seq_len, kv_loc)
@@ -538,6 +544,76 @@ attn_fn pick_attention(int head_size, bool flash, size_t *smem) {
     return f2;
 }
 
+typedef void (*cluster_fn_t)(const ClusterParams);
+template <int U8, int U32>
+cluster_fn_t pick_cluster_nf(int nf) {
+    switch (nf) {
+    case 1: return layers_cluster_kernel<1, U8, U32>;
+    case 2: return layers_cluster_kernel<2, U8, U32>;
+    case 3: return layers_cluster_kernel<3, U8, U32>;
+    case 4: return layers_cluster_kernel<4, U8, U32>;
+    case 6: return layers_cluster_kernel<6, U8, U32>;
+    case 8: return layers_cluster_kernel<8, U8, U32>;
+    default: return nullptr;
+    }
+}
+cluster_fn_t pick_cluster(int dim, int hidden, int head_size) {
+    const int hs4 = head_size / 4;
+    const int lpr = (hs4 % 8 == 0) ? 8 : (hs4 % 4 == 0) ? 4 : (hs4 % 2 == 0) ? 2 : 1;
+    const int nf = hs4 / lpr;
+    const int u8 = (dim / 4 + 7) / 8, u32 = (hidden / 4 + 31) / 32;
+    if (u8 > CL_MAXU || u32 > CL_MAXU) return nullptr;
+    if (u8 <= 9 && u32 <= 6) return pick_cluster_nf<9, 6>(nf);      // stories15M: dim 288, hidden 768
+    return pick_cluster_nf<CL_MAXU, CL_MAXU>(nf);
+}
+size_t cluster_smem_bytes(const l2b_ctx *ctx, int C) {
+    const int dim = ctx->dim, hid = ctx->hid_loc, hs = ctx->head_size;
+    auto per = [&](int rows) { int v = (rows + C - 1) / C; return v + (v & 1); };
+    const int hs4 = hs / 4;
+    const int lpr = (hs4 % 8 == 0) ? 8 : (hs4 % 4 == 0) ? 4 : (hs4 % 2 == 0) ? 2 : 1;
+    const int ng = NWARP * (32 / lpr);
+    const int hpc = (ctx->heads_loc + C - 1) / C;
+    size_t f = (size_t)dim + (dim > hid ? dim : hid) + cl_round4(per(dim + 2 * ctx->kv_loc)) + (size_t)hpc * hs +
+               cl_round4(per(dim)) + cl_round4(per(hid)) + (size_t)ng * hs + 2 * ng + cl_round4(ng) + hs;
+    return f * sizeof(float);
+}
+
+// all layers of one step in one cluster launch (small models)
+int launch_cluster_layers(l2b_ctx *ctx, cudaStream_t st) {
+    if (ctx->profiling) {
+        const int hpos = ctx->n_appended > 0 ? ctx->n_appended - 1 : 0;
+        const uint64_t L = ctx->cfg.n_layers, dim = ctx->dim;
+        const uint64_t bytes = 4ull * L * (dim * dim * 2 + 2ull * ctx->kv_loc * dim + 3ull * ctx->hid_loc * dim + 2 * dim) +
+                               4ull * L * 2 * (uint64_t)(hpos + 1) * ctx->kv_loc;
+        int prc = prof_mark(ctx, "layers", -1, bytes, st);
+        if (prc) return prc;
+    }
+    ClusterParams q{};
+    q.emb = ctx->emb; q.rms_att = ctx->rms_att; q.rms_ffn = ctx->rms_ffn;
+    q.wq = ctx->wq; q.wk = ctx->wk; q.wv = ctx->wv; q.wo = ctx->wo; q.w1 = ctx->w1; q.w2 = ctx->w2; q.w3 = ctx->w3;
+    q.kcache = ctx->kcache; q.vcache = ctx->vcache;
+    q.rope_cos = ctx->rope_cos; q.rope_sin = ctx->rope_sin;
+    q.ctl = ctx->ctl;
+    q.x_out = ctx->X;
+    q.dim = ctx->dim; q.hidden = ctx->hid_loc; q.n_layers = ctx->cfg.n_layers; q.n_heads = ctx->heads_loc;
+    q.kv_mul = ctx->kv_mul; q.head_size = ctx->head_size; q.kv_dim = ctx->kv_loc; q.seq_len = ctx->cfg.seq_len;
+    q.bump_epoch = 1;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(ctx->cluster_C);
+    lc.blockDim = dim3(NT);
+    lc.dynamicSmemBytes = ctx->cluster_smem;
+    lc.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = ctx->cluster_C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1] = pdl_attr();
+    lc.attrs = at;
+    lc.numAttrs = ctx->use_pdl ? 2 : 1;
+    L2B_CUDA(ctx, cudaLaunchKernelEx(&lc, ctx->cluster_fn, q));
+    ++ctx->last_launches;
+    return L2B_OK;
+}
+
 typedef void (*attn_wo_fn)(const AttnWoParams);
 attn_wo_fn pick_attn_wo(int head_size, size_t *smem) {
     const int hs4 = head_size / 4;
@@ -746,6 +822,11 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, StepMode mode) {
     float *Xc = ctx->X, *Xo = ctx->Xalt;
     const float *pend = nullptr;             // partial vectors still to be folded into x
     int npend = 0;
+    const int first_layer = ctx->use_cluster ? c.n_layers : 0;   // cluster kernel: every layer in one launch
+    if (ctx->use_cluster) {
+        int rc = launch_cluster_layers(ctx, st);
+        if (rc) return rc;
+    }
     auto fold_pending = [&](GemvParams &g) {
         g.x_in = Xc;
         if (pend) {
@@ -754,7 +835,7 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, StepMode mode) {
             pend = nullptr; npend = 0;
         }
     };
-    for (int l = 0; l < c.n_layers; ++l) {
+    for (int l = first_layer; l < c.n_layers; ++l) {
         // ---- rmsnorm + q,k,v + RoPE + KV append (:305-358)
         GemvParams p{};
         p.ctl = ctx->ctl;
@@ -1084,6 +1165,39 @@ int create_rank(l2b_ctx *ctx, const l2b_config *cfg, const Source &src, const fl
         ctx->fuse_ffn = (want & 2) && world == 1 && dim <= 8 * FFN_MAXU * 4 && hid % FFN_HSZ == 0;
         const char *er = getenv("L2B_ATTN_R");
         ctx->attn_R = er && atoi(er) >= 1 && atoi(er) <= 8 ? atoi(er) : 8;
+        // stories15M-class models: all layers in one 16-CTA cluster kernel (csrc/l2b_cluster.cuh)
+        {
+            const char *ec = getenv("L2B_CLUSTER");
+            const int wantc = ec ? atoi(ec) : 16;                  // 0 = off, else the cluster size to try first
+            cluster_fn_t fn = pick_cluster((int)dim, (int)hid, (int)hs);
+            if (wantc > 0 && world == 1 && fn && dim <= 512) {
+                for (int C = wantc > CL_MAX_C ? CL_MAX_C : wantc; C >= 4 && !ctx->use_cluster; C /= 2) {
+                    const size_t smem = cluster_smem_bytes(ctx, C);
+                    if (smem > (size_t)kMaxSmemOptin) continue;
+                    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                        (C > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) {
+                        cudaGetLastError();
+                        continue;
+                    }
+                    cudaLaunchConfig_t lc{};
+                    lc.gridDim = dim3(C); lc.blockDim = dim3(NT); lc.dynamicSmemBytes = smem;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    lc.attrs = at; lc.numAttrs = 1;
+                    int nclusters = 0;
+                    if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &lc) == cudaSuccess && nclusters >= 1) {
+                        ctx->use_cluster = true;
+                        ctx->cluster_C = C;
+                        ctx->cluster_fn = fn;
+                        ctx->cluster_smem = smem;
+                    } else {
+                        cudaGetLastError();
+                    }
+                }
+            }
+            if (ctx->use_cluster) { ctx->fuse_attn = false; ctx->fuse_ffn = false; }
+        }
         if (ctx->fuse_attn) L2B_TRY(dev_alloc(ctx, &ctx->attn_parts, (size_t)cfg->n_heads * dim));
         if (ctx->fuse_ffn) L2B_TRY(dev_alloc(ctx, &ctx->ffn_parts, (size_t)(hid / FFN_HSZ) * dim));
     }
