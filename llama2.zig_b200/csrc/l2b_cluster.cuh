@@ -40,6 +40,7 @@ struct ClusterParams {
     float *x_out;                       // the residual stream after the last layer (input of the classifier kernel)
     int dim, hidden, n_layers, n_heads, kv_mul, head_size, kv_dim, seq_len;
     int bump_epoch;
+    unsigned long long *trace;          // L2B_TRACE=1: [n_layers][16] phase stamps of CTA 0 (ns)
 };
 
 // one (row pair) x (TPR lanes) dot-product tile: weights of rows (v0, v0+1) in registers
@@ -92,22 +93,30 @@ __device__ __forceinline__ void cl_dot(const ClTile<TPR, U> &t, const float4 *xs
     }
 }
 
-// rmsnorm of src (n floats, shared memory) with gain g (global) into dst (shared memory); all NT threads
-__device__ __forceinline__ void cl_rmsnorm(float *dst, const float *src, const float *g, int n, float *scratch) {
+// rmsnorm of src (n <= 2 * NT floats, shared memory) into dst (shared memory); the gain of elements
+// tid and tid + NT is already in registers (fetched a phase earlier: its L2 round trip is hidden)
+__device__ __forceinline__ void cl_rmsnorm(float *dst, const float *src, const float (&g)[2], int n, float *scratch) {
     const int tid = threadIdx.x;
-    float ssq = 0.0f;
-    for (int i = tid; i < n; i += NT) ssq = fmaf(src[i], src[i], ssq);
+    const float v0 = tid < n ? src[tid] : 0.0f, v1 = tid + NT < n ? src[tid + NT] : 0.0f;
+    float ssq = fmaf(v0, v0, 0.0f);
+    ssq = fmaf(v1, v1, ssq);
     float ss = block_sum(ssq, scratch);
     ss /= (float)n;            // :452
     ss += 1e-5f;               // :453
     const float s = 1.0f / sqrtf(ss);   // :454
-    for (int i = tid; i < n; i += NT) dst[i] = __fmul_rn(__fmul_rn(src[i], s), __ldg(g + i));   // :462
+    if (tid < n) dst[tid] = __fmul_rn(__fmul_rn(v0, s), g[0]);            // :462
+    if (tid + NT < n) dst[tid + NT] = __fmul_rn(__fmul_rn(v1, s), g[1]);
     __syncthreads();
+}
+__device__ __forceinline__ void cl_load_gain(float (&g)[2], const float *gamma, int n) {
+    const int tid = threadIdx.x;
+    g[0] = tid < n ? __ldg(gamma + tid) : 0.0f;
+    g[1] = tid + NT < n ? __ldg(gamma + tid + NT) : 0.0f;
 }
 
 // NF: attention float4 per lane per row (head_size = 4 * NF * LPR); U8 >= ceil(dim/4/8) and
-// U32 >= ceil(hidden/4/32): float4 columns per lane of the two GEMV tile shapes (register arrays)
-template <int NF, int U8, int U32>
+// U16 >= ceil(hidden/4/16): float4 columns per lane of the two GEMV tile shapes (register arrays)
+template <int NF, int U8, int U16>
 __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterParams p) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -146,10 +155,45 @@ __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterPara
     const int LPR = hs4 / NF, RPW = 32 / LPR, NG = NWARP * RPW;
     float *accp = att, *mlp = accp + (size_t)NG * hs, *wgt = mlp + 2 * NG, *qh = wgt + cl_round4(NG);
 
-    // ---- the first weight tile of layer 0 does not depend on anything
-    ClTile<8, U8> t8;
-    const int grp8 = tid >> 3, sub8 = tid & 7;               // 32 row pairs per tile
+    // ---- everything immutable that layer 0 needs is requested before the dependency wait
+    ClTile<8, U8> t8, t8b;
+    const int grp8 = tid >> 3, sub8 = tid & 7;               // TPR = 8: 32 row pairs (64 rows) per tile
+    const int grp16 = tid >> 4, sub16 = tid & 15;            // TPR = 16: 16 row pairs (32 rows) per tile
+    const int hid4 = hidden >> 2;
     cl_issue<8, U8>(t8, [&](int v) { return cl_row_qkv(p, 0, v); }, q0 + 2 * grp8, q1, n4, sub8);
+    float g_att[2], g_ffn[2];
+    cl_load_gain(g_att, p.rms_att, dim);
+    cl_load_gain(g_ffn, p.rms_ffn, dim);
+
+    // gather plans (the same every layer): which peer's slice holds the float2 this thread fetches
+    constexpr int GX = 1, GH = 4;                             // dim <= 512 -> <= 256 pairs; hidden <= 2048 -> <= 1024 pairs
+    const float2 *gx_src[GX], *gxb_src[GX], *gh_src[GH];
+#pragma unroll
+    for (int k = 0; k < GX; ++k) {
+        const int e = 2 * (tid + k * NT);
+        gx_src[k] = gxb_src[k] = nullptr;
+        if (e < dim) {
+            const int ox = e / x_per;
+            gx_src[k] = reinterpret_cast<const float2 *>(cluster.map_shared_rank(o_x, ox) + (e - ox * x_per));
+            const int h = e / hs;
+            gxb_src[k] = reinterpret_cast<const float2 *>(cluster.map_shared_rank(o_xb, h % C) + ((h / C) * hs + e - h * hs));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < GH; ++k) {
+        const int e = 2 * (tid + k * NT);
+        gh_src[k] = nullptr;
+        if (e < hidden) {
+            const int oh = e / hb_per;
+            gh_src[k] = reinterpret_cast<const float2 *>(cluster.map_shared_rank(o_hb, oh) + (e - oh * hb_per));
+        }
+    }
+    auto gather_x = [&]() {
+#pragma unroll
+        for (int k = 0; k < GX; ++k)
+            if (gx_src[k]) reinterpret_cast<float2 *>(xres)[tid + k * NT] = *gx_src[k];
+        __syncthreads();
+    };
 
     pdl_launch_dependents();
     pdl_wait();
@@ -159,13 +203,30 @@ __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterPara
     const int T = pos + 1;
     const float root_hs = sqrtf((float)hs);
 
+    // RoPE factors of the row pair this thread finishes in the first q/k/v tile: the same rows every layer
+    float rope_c = 1.0f, rope_s = 0.0f;
+    {
+        const int v = q0 + 2 * grp8;
+        if (sub8 == 0 && v < q1 && v < dim + p.kv_dim) {
+            const int i = v < dim ? v : v - dim;
+            const int pr = (i % hs) >> 1;
+            rope_c = __ldg(p.rope_cos + (size_t)pos * (hs >> 1) + pr);
+            rope_s = __ldg(p.rope_sin + (size_t)pos * (hs >> 1) + pr);
+        }
+    }
     for (int i = tid; i < dim; i += NT) xres[i] = __ldg(p.emb + (size_t)token * dim + i);   // :295-296
     __syncthreads();
 
+    // attention lanes
+    const int LPRc = LPR;
+    const int lr = lane % LPRc, rw = lane / LPRc, agrp = warp * RPW + rw;
+
+#define CL_STAMP(k) do { if (p.trace && rank == 0 && tid == 0) p.trace[l * 16 + (k)] = global_ns(); } while (0)
     for (int l = 0; l < p.n_layers; ++l) {
         const size_t loff = (size_t)l * p.seq_len * p.kv_dim;
+        CL_STAMP(0);
         // =========== phase 1: rmsnorm + q,k,v rows + RoPE + KV append (:305-358)
-        cl_rmsnorm(vin, xres, p.rms_att + (size_t)l * dim, dim, scratch);
+        cl_rmsnorm(vin, xres, g_att, dim, scratch);
         for (int v0 = q0; v0 < q1; v0 += 64) {               // 32 row pairs per tile
             const int v = v0 + 2 * grp8;
             if (v0 != q0) cl_issue<8, U8>(t8, [&](int vv) { return cl_row_qkv(p, l, vv); }, v, q1, n4, sub8);
@@ -175,9 +236,12 @@ __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterPara
                 if (v < dim + p.kv_dim) {                     // q or k: rotate the adjacent pair (:336-351)
                     const bool is_q = v < dim;
                     const int i = is_q ? v : v - dim;
-                    const int pr = (i % hs) >> 1;
-                    const float fcr = __ldg(p.rope_cos + (size_t)pos * (hs >> 1) + pr);
-                    const float fci = __ldg(p.rope_sin + (size_t)pos * (hs >> 1) + pr);
+                    float fcr = rope_c, fci = rope_s;
+                    if (v0 != q0) {
+                        const int pr = (i % hs) >> 1;
+                        fcr = __ldg(p.rope_cos + (size_t)pos * (hs >> 1) + pr);
+                        fci = __ldg(p.rope_sin + (size_t)pos * (hs >> 1) + pr);
+                    }
                     const float r0v = __fsub_rn(__fmul_rn(a0, fcr), __fmul_rn(a1, fci));     // :348
                     const float r1v = __fadd_rn(__fmul_rn(a0, fci), __fmul_rn(a1, fcr));     // :349
                     if (is_q) { o_qkv[v - q0] = r0v; o_qkv[v - q0 + 1] = r1v; }
@@ -188,11 +252,22 @@ __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterPara
                 }
             }
         }
-        // request my first wo tile (immutable) before the barrier
-        ClTile<8, U8> t8b;
+        // requested before the barrier: my first wo tile, and (attention CTAs) the cache rows of the
+        // earlier positions for my head's first pass - only the row of `pos` itself is new
         cl_issue<8, U8>(t8b, [&](int v) { return p.wo + ((size_t)l * dim + v) * dim; }, x0 + 2 * grp8, x1, n4, sub8);
+        float4 kk0[NF], vv0[NF];
+        const bool pre_ok = rank < p.n_heads && agrp < pos;   // row t = agrp of head `rank`, already in the cache
+        if (pre_ok) {
+            const size_t hoff0 = (size_t)(rank / p.kv_mul) * hs;
+            const float4 *k4 = reinterpret_cast<const float4 *>(p.kcache + loff + hoff0 + (size_t)agrp * p.kv_dim);
+            const float4 *v4 = reinterpret_cast<const float4 *>(p.vcache + loff + hoff0 + (size_t)agrp * p.kv_dim);
+#pragma unroll
+            for (int f = 0; f < NF; ++f) { kk0[f] = __ldcg(k4 + lr + f * LPRc); vv0[f] = __ldcg(v4 + lr + f * LPRc); }
+        }
         __threadfence();                                      // k / v rows visible to the attention CTAs
+        CL_STAMP(1);
         cluster.sync();
+        CL_STAMP(2);
 
         // =========== phase 2: attention, head h on CTA h (:361-389)
         for (int h = rank; h < p.n_heads; h += C) {
@@ -204,25 +279,29 @@ __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterPara
             }
             __syncthreads();
             const float4 *q4 = reinterpret_cast<const float4 *>(qh);
-            const int lr = lane % LPR, rw = lane / LPR, grp = warp * RPW + rw;
             const size_t hoff = (size_t)(h / p.kv_mul) * hs;
             const float *kb = p.kcache + loff + hoff, *vb = p.vcache + loff + hoff;
             float4 qf[NF], acc[NF];
 #pragma unroll
-            for (int f = 0; f < NF; ++f) { qf[f] = q4[lr + f * LPR]; acc[f] = make_float4(0.f, 0.f, 0.f, 0.f); }
+            for (int f = 0; f < NF; ++f) { qf[f] = q4[lr + f * LPRc]; acc[f] = make_float4(0.f, 0.f, 0.f, 0.f); }
             float m = -INFINITY, lsum = 0.0f;
             for (int tb = warp * RPW; tb < T; tb += NG) {     // warp-uniform bound
                 const int t = tb + rw;
                 const bool valid = t < T;
                 float4 kk[NF], vv[NF];
-                const float4 *k4 = reinterpret_cast<const float4 *>(kb + (size_t)(valid ? t : 0) * p.kv_dim);
-                const float4 *v4 = reinterpret_cast<const float4 *>(vb + (size_t)(valid ? t : 0) * p.kv_dim);
+                if (h == rank && tb == warp * RPW && pre_ok) {
 #pragma unroll
-                for (int f = 0; f < NF; ++f) { kk[f] = __ldcg(k4 + lr + f * LPR); vv[f] = __ldcg(v4 + lr + f * LPR); }
+                    for (int f = 0; f < NF; ++f) { kk[f] = kk0[f]; vv[f] = vv0[f]; }
+                } else {
+                    const float4 *k4 = reinterpret_cast<const float4 *>(kb + (size_t)(valid ? t : 0) * p.kv_dim);
+                    const float4 *v4 = reinterpret_cast<const float4 *>(vb + (size_t)(valid ? t : 0) * p.kv_dim);
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) { kk[f] = __ldcg(k4 + lr + f * LPRc); vv[f] = __ldcg(v4 + lr + f * LPRc); }
+                }
                 float sc = 0.0f;
 #pragma unroll
                 for (int f = 0; f < NF; ++f) sc = dot4(kk[f], qf[f], sc);
-                for (int o = LPR >> 1; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+                for (int o = LPRc >> 1; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
                 if (valid) {
                     sc = sc / root_hs;                        // :372
                     const float mn = fmaxf(m, sc);
@@ -239,8 +318,8 @@ __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterPara
                 }
             }
 #pragma unroll
-            for (int f = 0; f < NF; ++f) reinterpret_cast<float4 *>(accp + (size_t)grp * hs)[lr + f * LPR] = acc[f];
-            if (lr == 0) { mlp[2 * grp] = m; mlp[2 * grp + 1] = lsum; }
+            for (int f = 0; f < NF; ++f) reinterpret_cast<float4 *>(accp + (size_t)agrp * hs)[lr + f * LPRc] = acc[f];
+            if (lr == 0) { mlp[2 * agrp] = m; mlp[2 * agrp + 1] = lsum; }
             __syncthreads();
             if (warp == 0) {
                 float M = -INFINITY;
@@ -263,13 +342,14 @@ __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterPara
             }
             __syncthreads();
         }
+        CL_STAMP(3);
         cluster.sync();
+        CL_STAMP(4);
 
         // =========== phase 3: gather xb; my rows of wo; x slice += (:392-395)
-        for (int i = tid; i < dim; i += NT) {
-            const int h = i / hs;
-            vin[i] = cluster.map_shared_rank(o_xb, h % C)[(h / C) * hs + i - h * hs];
-        }
+#pragma unroll
+        for (int k = 0; k < GX; ++k)
+            if (gxb_src[k]) reinterpret_cast<float2 *>(vin)[tid + k * NT] = *gxb_src[k];
         __syncthreads();
         for (int v0 = x0; v0 < x1; v0 += 64) {
             const int v = v0 + 2 * grp8;
@@ -281,48 +361,52 @@ __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterPara
                 if (v + 1 < x1) o_x[v - x0 + 1] = xres[v + 1] + a1;
             }
         }
-        // first (w1, w3) tile for phase 4
-        cl_issue<8, U8>(t8, [&](int vv) { return ((vv & 1) ? p.w3 : p.w1) + ((size_t)l * hidden + (vv >> 1)) * dim; },
-                    2 * h0 + 2 * grp8, 2 * h1, n4, sub8);
+        // the first TWO (w1, w3) tiles for phase 4 (stories15M: 96 virtual rows per CTA = 1.5 tiles)
+        auto w13_row = [&](int vv) { return ((vv & 1) ? p.w3 : p.w1) + ((size_t)l * hidden + (vv >> 1)) * dim; };
+        cl_issue<8, U8>(t8, w13_row, 2 * h0 + 2 * grp8, 2 * h1, n4, sub8);
+        cl_issue<8, U8>(t8b, w13_row, 2 * h0 + 64 + 2 * grp8, 2 * h1, n4, sub8);
+        CL_STAMP(5);
         cluster.sync();
-        for (int i = tid; i < dim; i += NT) {
-            const int owner = i / x_per;
-            xres[i] = cluster.map_shared_rank(o_x, owner)[i - owner * x_per];
-        }
-        __syncthreads();
+        CL_STAMP(6);
+        gather_x();
+        CL_STAMP(7);
 
         // =========== phase 4: rmsnorm + (w1, w3) row pairs + SiLU*mul (:398-416)
-        cl_rmsnorm(vin, xres, p.rms_ffn + (size_t)l * dim, dim, scratch);
-        for (int v0 = 2 * h0; v0 < 2 * h1; v0 += 64) {
+        cl_rmsnorm(vin, xres, g_ffn, dim, scratch);
+        for (int v0 = 2 * h0, k = 0; v0 < 2 * h1; v0 += 64, ++k) {
             const int v = v0 + 2 * grp8;
-            if (v0 != 2 * h0)
-                cl_issue<8, U8>(t8, [&](int vv) { return ((vv & 1) ? p.w3 : p.w1) + ((size_t)l * hidden + (vv >> 1)) * dim; },
-                            v, 2 * h1, n4, sub8);
+            if (k >= 2) cl_issue<8, U8>(t8, w13_row, v, 2 * h1, n4, sub8);
             float a0, a1;
-            cl_dot<8, U8>(t8, reinterpret_cast<const float4 *>(vin), n4, sub8, a0, a1);
+            if (k == 1) cl_dot<8, U8>(t8b, reinterpret_cast<const float4 *>(vin), n4, sub8, a0, a1);
+            else cl_dot<8, U8>(t8, reinterpret_cast<const float4 *>(vin), n4, sub8, a0, a1);
             if (sub8 == 0 && v < 2 * h1) {
                 const float sg = __fmul_rn(a0, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-a0))));   // :412
                 o_hb[(v >> 1) - h0] = __fmul_rn(sg, a1);                                      // :416
             }
         }
-        // first w2 tile for phase 5: 32 lanes per row pair (hidden columns), 8 row pairs per tile
-        ClTile<32, U32> t32;
-        const int grp32 = tid >> 5, hid4 = hidden >> 2;
-        cl_issue<32, U32>(t32, [&](int v) { return p.w2 + ((size_t)l * dim + v) * hidden; }, x0 + 2 * grp32, x1, hid4, lane);
+        // first w2 tile for phase 5: 16 lanes per row pair over the hidden columns, 32 rows per tile;
+        // and the gains of the next layer
+        ClTile<16, U16> t16;
+        cl_issue<16, U16>(t16, [&](int v) { return p.w2 + ((size_t)l * dim + v) * hidden; }, x0 + 2 * grp16, x1, hid4, sub16);
+        if (l + 1 < p.n_layers) {
+            cl_load_gain(g_att, p.rms_att + (size_t)(l + 1) * dim, dim);
+            cl_load_gain(g_ffn, p.rms_ffn + (size_t)(l + 1) * dim, dim);
+        }
+        CL_STAMP(8);
         cluster.sync();
+        CL_STAMP(9);
 
         // =========== phase 5: gather hb; my rows of w2; x slice += (:419-422)
-        for (int i = tid; i < hidden; i += NT) {
-            const int owner = i / hb_per;
-            vin[i] = cluster.map_shared_rank(o_hb, owner)[i - owner * hb_per];
-        }
+#pragma unroll
+        for (int k = 0; k < GH; ++k)
+            if (gh_src[k]) reinterpret_cast<float2 *>(vin)[tid + k * NT] = *gh_src[k];
         __syncthreads();
-        for (int v0 = x0; v0 < x1; v0 += 16) {
-            const int v = v0 + 2 * grp32;
-            if (v0 != x0) cl_issue<32, U32>(t32, [&](int vv) { return p.w2 + ((size_t)l * dim + vv) * hidden; }, v, x1, hid4, lane);
+        for (int v0 = x0; v0 < x1; v0 += 32) {
+            const int v = v0 + 2 * grp16;
+            if (v0 != x0) cl_issue<16, U16>(t16, [&](int vv) { return p.w2 + ((size_t)l * dim + vv) * hidden; }, v, x1, hid4, sub16);
             float a0, a1;
-            cl_dot<32, U32>(t32, reinterpret_cast<const float4 *>(vin), hid4, lane, a0, a1);
-            if (lane == 0 && v < x1) {
+            cl_dot<16, U16>(t16, reinterpret_cast<const float4 *>(vin), hid4, sub16, a0, a1);
+            if (sub16 == 0 && v < x1) {
                 o_x[v - x0] = xres[v] + a0;
                 if (v + 1 < x1) o_x[v - x0 + 1] = xres[v + 1] + a1;
             }
@@ -330,13 +414,13 @@ __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterPara
         // first q/k/v tile of the next layer
         if (l + 1 < p.n_layers)
             cl_issue<8, U8>(t8, [&](int v) { return cl_row_qkv(p, l + 1, v); }, q0 + 2 * grp8, q1, n4, sub8);
+        CL_STAMP(10);
         cluster.sync();
-        for (int i = tid; i < dim; i += NT) {
-            const int owner = i / x_per;
-            xres[i] = cluster.map_shared_rank(o_x, owner)[i - owner * x_per];
-        }
-        __syncthreads();
+        CL_STAMP(11);
+        gather_x();
+        CL_STAMP(12);
     }
+#undef CL_STAMP
     if (rank == 0)
         for (int i = tid; i < dim; i += NT) p.x_out[i] = xres[i];
     cluster.sync();          // nobody leaves while a peer may still read its shared memory

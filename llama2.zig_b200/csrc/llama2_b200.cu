@@ -545,15 +545,15 @@ attn_fn pick_attention(int head_size, bool flash, size_t *smem) {
 }
 
 typedef void (*cluster_fn_t)(const ClusterParams);
-template <int U8, int U32>
+template <int U8, int U16>
 cluster_fn_t pick_cluster_nf(int nf) {
     switch (nf) {
-    case 1: return layers_cluster_kernel<1, U8, U32>;
-    case 2: return layers_cluster_kernel<2, U8, U32>;
-    case 3: return layers_cluster_kernel<3, U8, U32>;
-    case 4: return layers_cluster_kernel<4, U8, U32>;
-    case 6: return layers_cluster_kernel<6, U8, U32>;
-    case 8: return layers_cluster_kernel<8, U8, U32>;
+    case 1: return layers_cluster_kernel<1, U8, U16>;
+    case 2: return layers_cluster_kernel<2, U8, U16>;
+    case 3: return layers_cluster_kernel<3, U8, U16>;
+    case 4: return layers_cluster_kernel<4, U8, U16>;
+    case 6: return layers_cluster_kernel<6, U8, U16>;
+    case 8: return layers_cluster_kernel<8, U8, U16>;
     default: return nullptr;
     }
 }
@@ -561,10 +561,10 @@ cluster_fn_t pick_cluster(int dim, int hidden, int head_size) {
     const int hs4 = head_size / 4;
     const int lpr = (hs4 % 8 == 0) ? 8 : (hs4 % 4 == 0) ? 4 : (hs4 % 2 == 0) ? 2 : 1;
     const int nf = hs4 / lpr;
-    const int u8 = (dim / 4 + 7) / 8, u32 = (hidden / 4 + 31) / 32;
-    if (u8 > CL_MAXU || u32 > CL_MAXU) return nullptr;
-    if (u8 <= 9 && u32 <= 6) return pick_cluster_nf<9, 6>(nf);      // stories15M: dim 288, hidden 768
-    return pick_cluster_nf<CL_MAXU, CL_MAXU>(nf);
+    const int u8 = (dim / 4 + 7) / 8, u16 = (hidden / 4 + 15) / 16;
+    if (u8 > CL_MAXU || u16 > 2 * CL_MAXU || dim > 512 || hidden > 2048) return nullptr;
+    if (u8 <= 9 && u16 <= 12) return pick_cluster_nf<9, 12>(nf);    // stories15M: dim 288, hidden 768
+    return pick_cluster_nf<CL_MAXU, 2 * CL_MAXU>(nf);
 }
 size_t cluster_smem_bytes(const l2b_ctx *ctx, int C) {
     const int dim = ctx->dim, hid = ctx->hid_loc, hs = ctx->head_size;
@@ -598,6 +598,7 @@ int launch_cluster_layers(l2b_ctx *ctx, cudaStream_t st) {
     q.dim = ctx->dim; q.hidden = ctx->hid_loc; q.n_layers = ctx->cfg.n_layers; q.n_heads = ctx->heads_loc;
     q.kv_mul = ctx->kv_mul; q.head_size = ctx->head_size; q.kv_dim = ctx->kv_loc; q.seq_len = ctx->cfg.seq_len;
     q.bump_epoch = 1;
+    q.trace = (ctx->trace && !ctx->profiling) ? ctx->trace : nullptr;
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(ctx->cluster_C);
     lc.blockDim = dim3(NT);
