@@ -20,7 +20,6 @@
 #include <string>
 #include <vector>
 
-#include "l2b_cluster.cuh"
 #include "l2b_device.cuh"
 #include "l2b_prefill.cuh"
 
@@ -106,8 +105,8 @@ struct l2b_ctx {
     float *X = nullptr;                      // residual stream x; wo / w2 add into it (:395, :422)
     float *Xalt = nullptr;                   // second copy: kernels that fold partial vectors in write the new x here (ping-pong)
     float *final_X = nullptr;                // which of the two holds x after a step
-    float *attn_parts = nullptr, *ffn_parts = nullptr;   // small-model fusion: (n_heads, dim) and (hidden/32, dim) partial vectors
-    bool fuse_attn = false, fuse_ffn = false;
+    float *attn_parts = nullptr;             // small-model fusion: (n_heads, dim) partial vectors of attention + wo
+    bool fuse_attn = false;
     // batched prompt prefill (l2b_prefill, bandwidth-bound shapes): PF_MAXB positions per weight pass
     float *pf_x = nullptr, *pf_q = nullptr, *pf_xb = nullptr, *pf_hb = nullptr;   // [PF_MAXB][dim | q | q | hidden]
     float *pf_part_o = nullptr, *pf_part_ml = nullptr;
@@ -115,11 +114,6 @@ struct l2b_ctx {
     int *pf_tokens = nullptr;
     bool pf_ready = false, pf_ok = false;
     int attn_R = 1;                          // CTAs per head cluster of attn_wo_kernel
-    // small models: all layers of a step in one cluster kernel (csrc/l2b_cluster.cuh)
-    bool use_cluster = false;
-    int cluster_C = 16;
-    void (*cluster_fn)(const ClusterParams) = nullptr;
-    size_t cluster_smem = 0;
     float *delta = nullptr;                  // L2B_TP=nccl baseline only: partial rows before the NCCL all-reduce
     float *q = nullptr, *xb = nullptr, *hb = nullptr, *logits = nullptr, *logits_loc = nullptr;
     float *kcache = nullptr, *vcache = nullptr;     // (L, seq_len, kv_loc)
@@ -544,77 +538,6 @@ attn_fn pick_attention(int head_size, bool flash, size_t *smem) {
     return f2;
 }
 
-typedef void (*cluster_fn_t)(const ClusterParams);
-template <int U8, int U16>
-cluster_fn_t pick_cluster_nf(int nf) {
-    switch (nf) {
-    case 1: return layers_cluster_kernel<1, U8, U16>;
-    case 2: return layers_cluster_kernel<2, U8, U16>;
-    case 3: return layers_cluster_kernel<3, U8, U16>;
-    case 4: return layers_cluster_kernel<4, U8, U16>;
-    case 6: return layers_cluster_kernel<6, U8, U16>;
-    case 8: return layers_cluster_kernel<8, U8, U16>;
-    default: return nullptr;
-    }
-}
-cluster_fn_t pick_cluster(int dim, int hidden, int head_size) {
-    const int hs4 = head_size / 4;
-    const int lpr = (hs4 % 8 == 0) ? 8 : (hs4 % 4 == 0) ? 4 : (hs4 % 2 == 0) ? 2 : 1;
-    const int nf = hs4 / lpr;
-    const int u8 = (dim / 4 + 7) / 8, u16 = (hidden / 4 + 15) / 16;
-    if (u8 > CL_MAXU || u16 > 2 * CL_MAXU || dim > 512 || hidden > 2048) return nullptr;
-    if (u8 <= 9 && u16 <= 12) return pick_cluster_nf<9, 12>(nf);    // stories15M: dim 288, hidden 768
-    return pick_cluster_nf<CL_MAXU, 2 * CL_MAXU>(nf);
-}
-size_t cluster_smem_bytes(const l2b_ctx *ctx, int C) {
-    const int dim = ctx->dim, hid = ctx->hid_loc, hs = ctx->head_size;
-    auto per = [&](int rows) { int v = (rows + C - 1) / C; return v + (v & 1); };
-    const int hs4 = hs / 4;
-    const int lpr = (hs4 % 8 == 0) ? 8 : (hs4 % 4 == 0) ? 4 : (hs4 % 2 == 0) ? 2 : 1;
-    const int ng = NWARP * (32 / lpr);
-    const int hpc = (ctx->heads_loc + C - 1) / C;
-    size_t f = (size_t)dim + (dim > hid ? dim : hid) + cl_round4(per(dim + 2 * ctx->kv_loc)) + (size_t)hpc * hs +
-               cl_round4(per(dim)) + cl_round4(per(hid)) + (size_t)ng * hs + 2 * ng + cl_round4(ng) + hs;
-    return f * sizeof(float);
-}
-
-// all layers of one step in one cluster launch (small models)
-int launch_cluster_layers(l2b_ctx *ctx, cudaStream_t st) {
-    if (ctx->profiling) {
-        const int hpos = ctx->n_appended > 0 ? ctx->n_appended - 1 : 0;
-        const uint64_t L = ctx->cfg.n_layers, dim = ctx->dim;
-        const uint64_t bytes = 4ull * L * (dim * dim * 2 + 2ull * ctx->kv_loc * dim + 3ull * ctx->hid_loc * dim + 2 * dim) +
-                               4ull * L * 2 * (uint64_t)(hpos + 1) * ctx->kv_loc;
-        int prc = prof_mark(ctx, "layers", -1, bytes, st);
-        if (prc) return prc;
-    }
-    ClusterParams q{};
-    q.emb = ctx->emb; q.rms_att = ctx->rms_att; q.rms_ffn = ctx->rms_ffn;
-    q.wq = ctx->wq; q.wk = ctx->wk; q.wv = ctx->wv; q.wo = ctx->wo; q.w1 = ctx->w1; q.w2 = ctx->w2; q.w3 = ctx->w3;
-    q.kcache = ctx->kcache; q.vcache = ctx->vcache;
-    q.rope_cos = ctx->rope_cos; q.rope_sin = ctx->rope_sin;
-    q.ctl = ctx->ctl;
-    q.x_out = ctx->X;
-    q.dim = ctx->dim; q.hidden = ctx->hid_loc; q.n_layers = ctx->cfg.n_layers; q.n_heads = ctx->heads_loc;
-    q.kv_mul = ctx->kv_mul; q.head_size = ctx->head_size; q.kv_dim = ctx->kv_loc; q.seq_len = ctx->cfg.seq_len;
-    q.bump_epoch = 1;
-    q.trace = (ctx->trace && !ctx->profiling) ? ctx->trace : nullptr;
-    cudaLaunchConfig_t lc{};
-    lc.gridDim = dim3(ctx->cluster_C);
-    lc.blockDim = dim3(NT);
-    lc.dynamicSmemBytes = ctx->cluster_smem;
-    lc.stream = st;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = ctx->cluster_C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    at[1] = pdl_attr();
-    lc.attrs = at;
-    lc.numAttrs = ctx->use_pdl ? 2 : 1;
-    L2B_CUDA(ctx, cudaLaunchKernelEx(&lc, ctx->cluster_fn, q));
-    ++ctx->last_launches;
-    return L2B_OK;
-}
-
 typedef void (*attn_wo_fn)(const AttnWoParams);
 attn_wo_fn pick_attn_wo(int head_size, size_t *smem) {
     const int hs4 = head_size / 4;
@@ -670,32 +593,6 @@ int launch_attn_wo(l2b_ctx *ctx, int layer, cudaStream_t st) {
     lc.attrs = at;
     lc.numAttrs = ctx->use_pdl ? 2 : 1;
     L2B_CUDA(ctx, cudaLaunchKernelEx(&lc, fn, q));
-    ++ctx->last_launches;
-    return L2B_OK;
-}
-
-// rmsnorm + w1/w3 + SiLU*mul + w2 of one layer in one launch (dim <= 512): partial vectors -> ctx->ffn_parts
-int launch_ffn_fused(l2b_ctx *ctx, int layer, const GemvParams &g, cudaStream_t st) {
-    const uint64_t bytes = 3ull * ctx->hid_loc * ctx->dim * 4ull;
-    int prc = prof_mark(ctx, "ffn", layer, bytes, st);
-    if (prc) return prc;
-    FfnParams q{};
-    q.g = g;
-    q.g.spin_ns = ctx->spin_ns;
-    q.w1 = ctx->w1 + (size_t)layer * ctx->hid_loc * ctx->dim;
-    q.w3 = ctx->w3 + (size_t)layer * ctx->hid_loc * ctx->dim;
-    q.w2 = ctx->w2 + (size_t)layer * ctx->dim * ctx->hid_loc;
-    q.out_parts = ctx->ffn_parts;
-    q.hidden = ctx->hid_loc;
-    cudaLaunchConfig_t lc{};
-    lc.gridDim = dim3(ctx->hid_loc / FFN_HSZ);
-    lc.blockDim = dim3(NT);
-    lc.dynamicSmemBytes = (size_t)ctx->dim * 4 * 3;
-    lc.stream = st;
-    cudaLaunchAttribute at[1] = {pdl_attr()};
-    lc.attrs = at;
-    lc.numAttrs = ctx->use_pdl ? 1 : 0;
-    L2B_CUDA(ctx, cudaLaunchKernelEx(&lc, ffn_fused_kernel, q));
     ++ctx->last_launches;
     return L2B_OK;
 }
@@ -817,17 +714,13 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, StepMode mode) {
         }
         return rc;
     };
-    // small-model fusion (world == 1): attention+wo and the whole FFN leave their result as partial
-    // vectors that the NEXT kernel's prologue sums into x; such a kernel reads x from one buffer and
-    // CTA 0 writes the new x to the other (ping-pong), everything else updates x in place
+    // small-model fusion (world == 1): attention+wo leaves its result as one partial vector per head
+    // that the NEXT kernel's prologue sums into x; such a kernel reads x from one buffer and CTA 0
+    // writes the new x to the other (ping-pong), everything else updates x in place
     float *Xc = ctx->X, *Xo = ctx->Xalt;
     const float *pend = nullptr;             // partial vectors still to be folded into x
     int npend = 0;
-    const int first_layer = ctx->use_cluster ? c.n_layers : 0;   // cluster kernel: every layer in one launch
-    if (ctx->use_cluster) {
-        int rc = launch_cluster_layers(ctx, st);
-        if (rc) return rc;
-    }
+
     auto fold_pending = [&](GemvParams &g) {
         g.x_in = Xc;
         if (pend) {
@@ -836,7 +729,7 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, StepMode mode) {
             pend = nullptr; npend = 0;
         }
     };
-    for (int l = first_layer; l < c.n_layers; ++l) {
+    for (int l = 0; l < c.n_layers; ++l) {
         // ---- rmsnorm + q,k,v + RoPE + KV append (:305-358)
         GemvParams p{};
         p.ctl = ctx->ctl;
@@ -887,14 +780,6 @@ int enqueue_step(l2b_ctx *ctx, cudaStream_t st, StepMode mode) {
         f.n = dim;
         fold_pending(f);
         f.gamma = ctx->rms_ffn + (size_t)l * dim;
-        if (ctx->fuse_ffn && l + 1 < c.n_layers) {
-            // ---- ... + w2 in the same launch (:419); the last layer stays unfused so that the
-            // classifier's many CTAs stage a finished x instead of each summing the partial vectors
-            rc = launch_ffn_fused(ctx, l, f, st);
-            if (rc) return rc;
-            pend = ctx->ffn_parts; npend = ctx->hid_loc / FFN_HSZ;
-            continue;
-        }
         f.w0 = ctx->w1 + (size_t)l * ctx->hid_loc * dim;
         f.w1 = ctx->w3 + (size_t)l * ctx->hid_loc * dim;
         f.rows0 = ctx->hid_loc;
@@ -1076,7 +961,6 @@ int preload_kernels(l2b_ctx *ctx) {
     size_t smem = 0;
     L2B_CUDA(ctx, cudaFuncGetAttributes(&fa, (const void *)pick_attention(ctx->head_size, true, &smem)));
     if (pick_attn_wo(ctx->head_size, &smem)) L2B_CUDA(ctx, cudaFuncGetAttributes(&fa, (const void *)pick_attn_wo(ctx->head_size, &smem)));
-    L2B_CUDA(ctx, cudaFuncGetAttributes(&fa, (const void *)ffn_fused_kernel));
     const void *others[] = {(const void *)attention_kernel, (const void *)advance_kernel, (const void *)gather_logits_kernel,
                             (const void *)resid_add_kernel, (const void *)sample_prep_kernel, (const void *)synth_fill_kernel};
     for (const void *f : others) L2B_CUDA(ctx, cudaFuncGetAttributes(&fa, f));
@@ -1158,49 +1042,14 @@ int create_rank(l2b_ctx *ctx, const l2b_config *cfg, const Source &src, const fl
     {
         // small-model fusion (measured on B200, profiles/r02_small_models.md): attention + wo as one
         // cluster kernel (8 CTAs per head) is +7 % on stories15M (31 -> 25 kernels per token) and -1 % on
-        // stories110M, so it is on for dim <= 512 only; the fused FFN kernel is slower everywhere (off)
+        // stories110M, so it is on for dim <= 512 only (L2B_FUSE=0|1 overrides)
         const char *ef = getenv("L2B_FUSE");
-        const int want = ef ? atoi(ef) : (dim <= 512 ? 1 : 0);     // bit 0: attention+wo, bit 1: FFN
+        const int want = ef ? atoi(ef) : (dim <= 512 ? 1 : 0);
         size_t smem_aw = 0;
         ctx->fuse_attn = (want & 1) && world == 1 && dim < 1024 && pick_attn_wo((int)hs, &smem_aw) != nullptr;
-        ctx->fuse_ffn = (want & 2) && world == 1 && dim <= 8 * FFN_MAXU * 4 && hid % FFN_HSZ == 0;
         const char *er = getenv("L2B_ATTN_R");
         ctx->attn_R = er && atoi(er) >= 1 && atoi(er) <= 8 ? atoi(er) : 8;
-        // stories15M-class models: all layers in one 16-CTA cluster kernel (csrc/l2b_cluster.cuh)
-        {
-            const char *ec = getenv("L2B_CLUSTER");
-            const int wantc = ec ? atoi(ec) : 16;                  // 0 = off, else the cluster size to try first
-            cluster_fn_t fn = pick_cluster((int)dim, (int)hid, (int)hs);
-            if (wantc > 0 && world == 1 && fn && dim <= 512) {
-                for (int C = wantc > CL_MAX_C ? CL_MAX_C : wantc; C >= 4 && !ctx->use_cluster; C /= 2) {
-                    const size_t smem = cluster_smem_bytes(ctx, C);
-                    if (smem > (size_t)kMaxSmemOptin) continue;
-                    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-                        (C > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) {
-                        cudaGetLastError();
-                        continue;
-                    }
-                    cudaLaunchConfig_t lc{};
-                    lc.gridDim = dim3(C); lc.blockDim = dim3(NT); lc.dynamicSmemBytes = smem;
-                    cudaLaunchAttribute at[1];
-                    at[0].id = cudaLaunchAttributeClusterDimension;
-                    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-                    lc.attrs = at; lc.numAttrs = 1;
-                    int nclusters = 0;
-                    if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &lc) == cudaSuccess && nclusters >= 1) {
-                        ctx->use_cluster = true;
-                        ctx->cluster_C = C;
-                        ctx->cluster_fn = fn;
-                        ctx->cluster_smem = smem;
-                    } else {
-                        cudaGetLastError();
-                    }
-                }
-            }
-            if (ctx->use_cluster) { ctx->fuse_attn = false; ctx->fuse_ffn = false; }
-        }
         if (ctx->fuse_attn) L2B_TRY(dev_alloc(ctx, &ctx->attn_parts, (size_t)cfg->n_heads * dim));
-        if (ctx->fuse_ffn) L2B_TRY(dev_alloc(ctx, &ctx->ffn_parts, (size_t)(hid / FFN_HSZ) * dim));
     }
     L2B_TRY(dev_alloc(ctx, &ctx->delta, dim));
     L2B_TRY(dev_alloc(ctx, &ctx->q, (size_t)ctx->q_loc));

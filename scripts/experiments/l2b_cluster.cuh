@@ -40,7 +40,7 @@ struct ClusterParams {
     float *x_out;                       // the residual stream after the last layer (input of the classifier kernel)
     int dim, hidden, n_layers, n_heads, kv_mul, head_size, kv_dim, seq_len;
     int bump_epoch;
-    unsigned long long *trace;          // L2B_TRACE=1: [n_layers][16] phase stamps of CTA 0 (ns)
+    unsigned long long *trace;          // L2B_TRACE=1: [n_layers][32] phase stamps of CTA 0 (ns)
 };
 
 // one (row pair) x (TPR lanes) dot-product tile: weights of rows (v0, v0+1) in registers
@@ -221,12 +221,13 @@ __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterPara
     const int LPRc = LPR;
     const int lr = lane % LPRc, rw = lane / LPRc, agrp = warp * RPW + rw;
 
-#define CL_STAMP(k) do { if (p.trace && rank == 0 && tid == 0) p.trace[l * 16 + (k)] = global_ns(); } while (0)
+#define CL_STAMP(k) do { if (p.trace && rank == 0 && tid == 0) p.trace[l * 32 + (k)] = global_ns(); } while (0)
     for (int l = 0; l < p.n_layers; ++l) {
         const size_t loff = (size_t)l * p.seq_len * p.kv_dim;
         CL_STAMP(0);
         // =========== phase 1: rmsnorm + q,k,v rows + RoPE + KV append (:305-358)
         cl_rmsnorm(vin, xres, g_att, dim, scratch);
+        CL_STAMP(16);
         for (int v0 = q0; v0 < q1; v0 += 64) {               // 32 row pairs per tile
             const int v = v0 + 2 * grp8;
             if (v0 != q0) cl_issue<8, U8>(t8, [&](int vv) { return cl_row_qkv(p, l, vv); }, v, q1, n4, sub8);
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterPara
                 }
             }
         }
+        CL_STAMP(17);
         // requested before the barrier: my first wo tile, and (attention CTAs) the cache rows of the
         // earlier positions for my head's first pass - only the row of `pos` itself is new
         cl_issue<8, U8>(t8b, [&](int v) { return p.wo + ((size_t)l * dim + v) * dim; }, x0 + 2 * grp8, x1, n4, sub8);
@@ -264,6 +266,7 @@ __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterPara
 #pragma unroll
             for (int f = 0; f < NF; ++f) { kk0[f] = __ldcg(k4 + lr + f * LPRc); vv0[f] = __ldcg(v4 + lr + f * LPRc); }
         }
+        CL_STAMP(18);
         __threadfence();                                      // k / v rows visible to the attention CTAs
         CL_STAMP(1);
         cluster.sync();
@@ -278,6 +281,7 @@ __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterPara
                 qh[tid] = cluster.map_shared_rank(o_qkv, owner)[v - owner * qkv_per];
             }
             __syncthreads();
+            CL_STAMP(19);
             const float4 *q4 = reinterpret_cast<const float4 *>(qh);
             const size_t hoff = (size_t)(h / p.kv_mul) * hs;
             const float *kb = p.kcache + loff + hoff, *vb = p.vcache + loff + hoff;
@@ -317,6 +321,7 @@ __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterPara
                     m = mn;
                 }
             }
+            CL_STAMP(20);
 #pragma unroll
             for (int f = 0; f < NF; ++f) reinterpret_cast<float4 *>(accp + (size_t)agrp * hs)[lr + f * LPRc] = acc[f];
             if (lr == 0) { mlp[2 * agrp] = m; mlp[2 * agrp + 1] = lsum; }
@@ -335,6 +340,7 @@ __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterPara
                 if (lane == 0) { sh_L = L; sh_M = M; }
             }
             __syncthreads();
+            CL_STAMP(21);
             if (tid < hs) {
                 float o = 0.0f;
                 for (int g = 0; g < NG; ++g) o = fmaf(wgt[g], accp[(size_t)g * hs + tid], o);
@@ -373,6 +379,7 @@ __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterPara
 
         // =========== phase 4: rmsnorm + (w1, w3) row pairs + SiLU*mul (:398-416)
         cl_rmsnorm(vin, xres, g_ffn, dim, scratch);
+        CL_STAMP(22);
         for (int v0 = 2 * h0, k = 0; v0 < 2 * h1; v0 += 64, ++k) {
             const int v = v0 + 2 * grp8;
             if (k >= 2) cl_issue<8, U8>(t8, w13_row, v, 2 * h1, n4, sub8);
@@ -384,6 +391,7 @@ __global__ void __launch_bounds__(NT, 1) layers_cluster_kernel(const ClusterPara
                 o_hb[(v >> 1) - h0] = __fmul_rn(sg, a1);                                      // :416
             }
         }
+        CL_STAMP(23);
         // first w2 tile for phase 5: 16 lanes per row pair over the hidden columns, 32 rows per tile;
         // and the gains of the next layer
         ClTile<16, U16> t16;
