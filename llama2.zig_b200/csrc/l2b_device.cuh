@@ -1265,11 +1265,39 @@ __global__ void __launch_bounds__(NT) attention_kernel(const AttnParams p) {
 //   online softmax: m' = max(m, s); l = l*e^(m-m') + e^(s-m'); acc = acc*e^(m-m') + e^(s-m') V_t
 //   out = sum_groups e^(m_g-M) acc_g / sum_groups e^(m_g-M) l_g    (== softmax(:687-706) . V, :657-685)
 // ---------------------------------------------------------------------------------------
+// Merge the online-softmax partials (m, l, acc) of the RPW row groups of ONE warp with xor shuffles
+// (lanes with equal column slice `lr`, different row group): log2(RPW) steps in a fixed tree order,
+// so only NWARP partials per CTA go through shared memory afterwards.  Measured r02 (cluster-kernel
+// phase trace): the previous all-groups-through-shared-memory merge (64 groups, then a 64-term serial
+// sum per output element) was 1.8 us of a 2.4 us attention.
+template <int NF>
+__device__ __forceinline__ void attn_warp_merge(float &m, float &l, float4 (&acc)[NF], int LPR) {
+    for (int off = LPR; off < 32; off <<= 1) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m, off);
+        const float lo = __shfl_xor_sync(0xffffffffu, l, off);
+        const float mn = fmaxf(m, mo);
+        const float ss = (m == -INFINITY) ? 0.0f : expf(m - mn);     // empty partials carry m = -inf, l = 0
+        const float so = (mo == -INFINITY) ? 0.0f : expf(mo - mn);
+        l = fmaf(l, ss, lo * so);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            const float ox = __shfl_xor_sync(0xffffffffu, acc[f].x, off);
+            const float oy = __shfl_xor_sync(0xffffffffu, acc[f].y, off);
+            const float oz = __shfl_xor_sync(0xffffffffu, acc[f].z, off);
+            const float ow = __shfl_xor_sync(0xffffffffu, acc[f].w, off);
+            acc[f].x = fmaf(acc[f].x, ss, ox * so);
+            acc[f].y = fmaf(acc[f].y, ss, oy * so);
+            acc[f].z = fmaf(acc[f].z, ss, oz * so);
+            acc[f].w = fmaf(acc[f].w, ss, ow * so);
+        }
+        m = mn;
+    }
+}
+
 template <int NF>   // float4 per lane per row: head_size = 4 * NF * LPR
 __global__ void __launch_bounds__(NT) attention_flash_kernel(const AttnParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int is_last;
-    __shared__ float sh_L;
     unsigned long long *atr = p.trace ? p.trace + ((size_t)blockIdx.y * gridDim.x) * TRACE_SLOTS : nullptr;
     if (threadIdx.x == 0) L2B_STAMP(atr, 0);
     pdl_launch_dependents();
@@ -1297,10 +1325,8 @@ __global__ void __launch_bounds__(NT) attention_flash_kernel(const AttnParams p)
     const int NG = NWARP * RPW;               // row groups in the CTA
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lr = lane % LPR, rw = lane / LPR;
-    const int grp = warp * RPW + rw;
     float *accp = reinterpret_cast<float *>(smem_raw);        // [NG][hs]
     float *mlp = accp + (size_t)NG * hs;                      // [NG][2]
-    float *wgt = mlp + 2 * NG;                                // [NG]
 
     const size_t hoff = (size_t)(h / p.kv_mul) * hs;          // :369, :382
     const float4 *q4 = reinterpret_cast<const float4 *>(qz + (size_t)h * hs);
@@ -1358,30 +1384,26 @@ __global__ void __launch_bounds__(NT) attention_flash_kernel(const AttnParams p)
         update(kc, vC, vc);
     }
 
-    // ---- merge the NG groups (fixed order => deterministic)
+    // ---- merge: row groups of a warp by shuffles, then the NWARP warps through shared memory (fixed
+    // order => deterministic)
+    attn_warp_merge<NF>(m, l, acc, LPR);
+    if (rw == 0) {
 #pragma unroll
-    for (int f = 0; f < NF; ++f)
-        reinterpret_cast<float4 *>(accp + (size_t)grp * hs)[lr + f * LPR] = acc[f];
-    if (lr == 0) { mlp[2 * grp] = m; mlp[2 * grp + 1] = l; }
-    __syncthreads();
-    if (warp == 0) {
-        float M = -INFINITY;
-        for (int g = lane; g < NG; g += 32) M = fmaxf(M, mlp[2 * g]);
-        M = warp_max(M);
-        float L = 0.0f;
-        for (int g = lane; g < NG; g += 32) {
-            const float w = expf(mlp[2 * g] - M);             // empty groups: e^(-inf) = 0
-            wgt[g] = w;
-            L = fmaf(w, mlp[2 * g + 1], L);
-        }
-        L = warp_sum(L);
-        if (lane == 0) { sh_L = L; mlp[0] = M; }              // mlp[0] reused to carry M (read after the barrier)
+        for (int f = 0; f < NF; ++f)
+            reinterpret_cast<float4 *>(accp + (size_t)warp * hs)[lr + f * LPR] = acc[f];
+        if (lr == 0) { mlp[2 * warp] = m; mlp[2 * warp + 1] = l; }
     }
     __syncthreads();
-    const float L = sh_L, M = mlp[0];
-    float o = 0.0f;
-    if (tid < hs)
-        for (int g = 0; g < NG; ++g) o = fmaf(wgt[g], accp[(size_t)g * hs + tid], o);
+    float M = -INFINITY;
+#pragma unroll
+    for (int g = 0; g < NWARP; ++g) M = fmaxf(M, mlp[2 * g]);
+    float L = 0.0f, o = 0.0f;
+#pragma unroll
+    for (int g = 0; g < NWARP; ++g) {                          // every thread: same order, same values
+        const float w = (mlp[2 * g] == -INFINITY) ? 0.0f : expf(mlp[2 * g] - M);
+        L = fmaf(w, mlp[2 * g + 1], L);
+        if (tid < hs) o = fmaf(w, accp[(size_t)g * hs + tid], o);
+    }
 
     if (active == 1) {
         if (tid < hs) xbz[(size_t)h * hs + tid] = o / L;
@@ -1450,13 +1472,11 @@ __global__ void __launch_bounds__(NT) attn_wo_kernel(const AttnWoParams q) {
     const int LPR = hs4 / NF, RPW = 32 / LPR, NG = NWARP * RPW;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lr = lane % LPR, rw = lane / LPR;
-    const int grp = warp * RPW + rw;
     float *accp = reinterpret_cast<float *>(smem_raw);        // [NG][hs]
     float *mlp = accp + (size_t)NG * hs;                      // [NG][2]
     float *wgt = mlp + 2 * NG;                                // [NG]
     float *tri = wgt + NG;                                    // [hs + 4]: this CTA's unnormalised out, M, L
     float *xbs = tri + hs + 4;                                // [hs]: merged head output
-    __shared__ float sh_L;
 
     // rows of the wo slice this CTA produces; the first pass of weights is immutable: fetch it now
     const int rows_per = (q.dim + R - 1) / R;
@@ -1527,30 +1547,28 @@ __global__ void __launch_bounds__(NT) attn_wo_kernel(const AttnWoParams q) {
         update(ka, vA, va);
         update(kc, vC, vc);
     }
-    // ---- merge the NG row groups of this CTA (fixed order)
+    // ---- merge: row groups of a warp by shuffles, then the NWARP warps through shared memory
+    attn_warp_merge<NF>(m, l, acc, LPR);
+    if (rw == 0) {
 #pragma unroll
-    for (int f = 0; f < NF; ++f)
-        reinterpret_cast<float4 *>(accp + (size_t)grp * hs)[lr + f * LPR] = acc[f];
-    if (lr == 0) { mlp[2 * grp] = m; mlp[2 * grp + 1] = l; }
-    __syncthreads();
-    if (warp == 0) {
-        float M = -INFINITY;
-        for (int g = lane; g < NG; g += 32) M = fmaxf(M, mlp[2 * g]);
-        M = warp_max(M);
-        float L = 0.0f;
-        for (int g = lane; g < NG; g += 32) {
-            const float w = (mlp[2 * g] == -INFINITY) ? 0.0f : expf(mlp[2 * g] - M);   // empty groups (and empty splits: M = -inf)
-            wgt[g] = w;
-            L = fmaf(w, mlp[2 * g + 1], L);
-        }
-        L = warp_sum(L);
-        if (lane == 0) { sh_L = L; tri[hs] = M; tri[hs + 1] = L; }
+        for (int f = 0; f < NF; ++f)
+            reinterpret_cast<float4 *>(accp + (size_t)warp * hs)[lr + f * LPR] = acc[f];
+        if (lr == 0) { mlp[2 * warp] = m; mlp[2 * warp + 1] = l; }
     }
     __syncthreads();
-    if (tid < hs) {
-        float o = 0.0f;
-        for (int g = 0; g < NG; ++g) o = fmaf(wgt[g], accp[(size_t)g * hs + tid], o);
-        tri[tid] = o;
+    {
+        float M = -INFINITY;
+#pragma unroll
+        for (int g = 0; g < NWARP; ++g) M = fmaxf(M, mlp[2 * g]);
+        float L = 0.0f, o = 0.0f;
+#pragma unroll
+        for (int g = 0; g < NWARP; ++g) {
+            const float w = (mlp[2 * g] == -INFINITY) ? 0.0f : expf(mlp[2 * g] - M);
+            L = fmaf(w, mlp[2 * g + 1], L);
+            if (tid < hs) o = fmaf(w, accp[(size_t)g * hs + tid], o);
+        }
+        if (tid < hs) tri[tid] = o;
+        if (tid == 0) { tri[hs] = M; tri[hs + 1] = L; }
     }
     // ---- merge the R timeline splits of the head through distributed shared memory
     cluster.sync();
