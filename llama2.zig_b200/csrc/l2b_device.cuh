@@ -1115,6 +1115,7 @@ struct AttnParams {
     // batched prompt prefill: gridDim.z positions at once; query z sits at position pos_base + z and
     // uses q / xb / partial buffers offset by z (pos_base < 0: single position from the control block)
     int pos_base, q_stride;
+    int seq_len;           // rows of the cache (bounds the speculative first pass; 0 = no speculation)
 };
 
 __device__ __forceinline__ int attn_lanes_per_row(int hs4) {
@@ -1303,10 +1304,46 @@ __global__ void __launch_bounds__(NT) attention_flash_kernel(const AttnParams p)
     pdl_launch_dependents();
     pdl_wait();
     if (threadIdx.x == 0) L2B_STAMP(atr, 2);
-    if (p.ctl[CTL_DONE]) return;
 
     const int h = blockIdx.x, s = blockIdx.y, z = blockIdx.z;
     const int hs = p.head_size, hs4 = hs >> 2;
+    const int LPR = hs4 / NF;                 // lanes per row (8, 4, 2 or 1)
+    const int RPW = 32 / LPR;                 // rows per warp pass
+    const int NG = NWARP * RPW;               // row groups in the CTA
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lr = lane % LPR, rw = lane / LPR;
+    const float *qz = p.q + (size_t)z * p.q_stride;
+    const size_t hoff = (size_t)(h / p.kv_mul) * hs;          // :369, :382
+    const float4 *q4 = reinterpret_cast<const float4 *>(qz + (size_t)h * hs);
+    const float *kb = p.kcache + hoff, *vb = p.vcache + hoff;
+
+    // Everything whose ADDRESS does not depend on the position is requested before the position is
+    // read from the control block: q, and (timeline split 0) the cache rows of this lane's first pass —
+    // rows beyond pos hold stale data and are masked below.  One L2 round trip less on the chain
+    // control word -> rows -> softmax (measured r02: attention is 2.7 us of a 13 us stories15M layer).
+    float4 qf[NF], acc[NF], ka[NF], vA[NF], kc[NF], vC[NF];
+    const int ta0 = warp * RPW + rw, tc0 = ta0 + NG;
+    const bool spec = (s == 0) && tc0 < p.seq_len;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        qf[f] = __ldcg(q4 + lr + f * LPR);
+        acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (spec) {
+        const float4 *ka4 = reinterpret_cast<const float4 *>(kb + (size_t)ta0 * p.kv_dim);
+        const float4 *va4 = reinterpret_cast<const float4 *>(vb + (size_t)ta0 * p.kv_dim);
+        const float4 *kc4 = reinterpret_cast<const float4 *>(kb + (size_t)tc0 * p.kv_dim);
+        const float4 *vc4 = reinterpret_cast<const float4 *>(vb + (size_t)tc0 * p.kv_dim);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            ka[f] = __ldcg(ka4 + lr + f * LPR);
+            vA[f] = __ldcg(va4 + lr + f * LPR);
+            kc[f] = __ldcg(kc4 + lr + f * LPR);
+            vC[f] = __ldcg(vc4 + lr + f * LPR);
+        }
+    }
+
+    if (p.ctl[CTL_DONE]) return;
     const int T = (p.pos_base >= 0 ? p.pos_base + z : p.ctl[CTL_POS]) + 1;
     int chunk = (T + p.nsplit - 1) / p.nsplit;
     if (chunk < p.min_chunk) chunk = p.min_chunk;
@@ -1314,31 +1351,13 @@ __global__ void __launch_bounds__(NT) attention_flash_kernel(const AttnParams p)
     if (s >= active) return;
     const int t0 = s * chunk;
     const int t1 = min(T, t0 + chunk);
-    const float *qz = p.q + (size_t)z * p.q_stride;
     float *xbz = p.xb + (size_t)z * p.q_stride;
     float *part_o_z = p.part_o + (size_t)z * gridDim.x * p.nsplit * hs;
     float *part_ml_z = p.part_ml + (size_t)z * gridDim.x * p.nsplit * 2;
     unsigned int *counters_z = p.counters + (size_t)z * gridDim.x;
-
-    const int LPR = hs4 / NF;                 // lanes per row (8, 4, 2 or 1)
-    const int RPW = 32 / LPR;                 // rows per warp pass
-    const int NG = NWARP * RPW;               // row groups in the CTA
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int lr = lane % LPR, rw = lane / LPR;
     float *accp = reinterpret_cast<float *>(smem_raw);        // [NG][hs]
     float *mlp = accp + (size_t)NG * hs;                      // [NG][2]
-
-    const size_t hoff = (size_t)(h / p.kv_mul) * hs;          // :369, :382
-    const float4 *q4 = reinterpret_cast<const float4 *>(qz + (size_t)h * hs);
-    const float *kb = p.kcache + hoff, *vb = p.vcache + hoff;
     const float root_hs = sqrtf((float)hs);
-
-    float4 qf[NF], acc[NF];
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-        qf[f] = __ldg(q4 + lr + f * LPR);
-        acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
     float m = -INFINITY, l = 0.0f;
 
     auto update = [&](const float4 (&kv)[NF], const float4 (&vv)[NF], bool valid) {
@@ -1368,17 +1387,18 @@ __global__ void __launch_bounds__(NT) attention_flash_kernel(const AttnParams p)
     for (int tbw = t0 + warp * RPW; tbw < t1; tbw += 2 * NG) {
         const int ta = tbw + rw, tc = ta + NG;
         const bool va = ta < t1, vc = tc < t1;
-        float4 ka[NF], vA[NF], kc[NF], vC[NF];
-        const float4 *ka4 = reinterpret_cast<const float4 *>(kb + (size_t)(va ? ta : t0) * p.kv_dim);
-        const float4 *va4 = reinterpret_cast<const float4 *>(vb + (size_t)(va ? ta : t0) * p.kv_dim);
-        const float4 *kc4 = reinterpret_cast<const float4 *>(kb + (size_t)(vc ? tc : t0) * p.kv_dim);
-        const float4 *vc4 = reinterpret_cast<const float4 *>(vb + (size_t)(vc ? tc : t0) * p.kv_dim);
+        if (!(spec && tbw == warp * RPW)) {                   // the first pass of split 0 is already in registers
+            const float4 *ka4 = reinterpret_cast<const float4 *>(kb + (size_t)(va ? ta : t0) * p.kv_dim);
+            const float4 *va4 = reinterpret_cast<const float4 *>(vb + (size_t)(va ? ta : t0) * p.kv_dim);
+            const float4 *kc4 = reinterpret_cast<const float4 *>(kb + (size_t)(vc ? tc : t0) * p.kv_dim);
+            const float4 *vc4 = reinterpret_cast<const float4 *>(vb + (size_t)(vc ? tc : t0) * p.kv_dim);
 #pragma unroll
-        for (int f = 0; f < NF; ++f) {
-            ka[f] = __ldg(ka4 + lr + f * LPR);
-            vA[f] = __ldg(va4 + lr + f * LPR);
-            kc[f] = __ldg(kc4 + lr + f * LPR);
-            vC[f] = __ldg(vc4 + lr + f * LPR);
+            for (int f = 0; f < NF; ++f) {
+                ka[f] = __ldcg(ka4 + lr + f * LPR);
+                vA[f] = __ldcg(va4 + lr + f * LPR);
+                kc[f] = __ldcg(kc4 + lr + f * LPR);
+                vC[f] = __ldcg(vc4 + lr + f * LPR);
+            }
         }
         update(ka, vA, va);
         update(kc, vC, vc);

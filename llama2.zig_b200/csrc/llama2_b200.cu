@@ -619,6 +619,7 @@ int launch_attention(l2b_ctx *ctx, int layer, cudaStream_t st) {
     a.nsplit = ctx->nsplit;
     a.min_chunk = ctx->min_chunk;
     a.pos_base = -1;
+    a.seq_len = ctx->cfg.seq_len;
     a.trace = trace_slot(ctx);
     size_t smem = ctx->attn_smem;
     attn_fn fn = pick_attention(ctx->head_size, ctx->attn_flash, &smem);
@@ -1669,7 +1670,7 @@ static int prefill_batched(l2b_ctx *ctx, const int32_t *tokens, int n_tokens, in
             a.xb = ctx->pf_xb; a.part_o = ctx->pf_part_o; a.part_ml = ctx->pf_part_ml; a.counters = ctx->pf_counters;
             a.head_size = ctx->head_size; a.kv_dim = ctx->kv_loc; a.kv_mul = ctx->kv_mul;
             a.nsplit = ctx->nsplit; a.min_chunk = ctx->min_chunk;
-            a.pos_base = pos; a.q_stride = ctx->q_loc;
+            a.pos_base = pos; a.q_stride = ctx->q_loc; a.seq_len = c.seq_len;
             cudaLaunchConfig_t lc{};
             lc.gridDim = dim3(ctx->heads_loc, ctx->nsplit, nb);
             lc.blockDim = dim3(NT);
@@ -2109,6 +2110,7 @@ int32_t l2b_op_attention_head(int32_t device, float *out, const float *q, const 
     a.counters = cnt; a.head_size = head_size; a.kv_dim = kv_stride; a.kv_mul = 1; a.nsplit = nsplit;
     a.min_chunk = 64;
     a.pos_base = -1;
+    a.seq_len = n_pos;
     int cap = (n_pos + nsplit - 1) / nsplit;
     if (cap < 64) cap = 64;
     const int G = NT / (head_size / 4);
