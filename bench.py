@@ -310,6 +310,11 @@ def run_workload(workload, args, rank, world, dist, sync, flush, clock_index):
         ck = l2b.read_checkpoint(real_path, mmap=False)
         t = l2b.Transformer(ck)
         data_desc, forced = "stories15M.bin (real checkpoint, -t 0)", None
+    elif args.in_process > 1:
+        ck = shape_checkpoint(shape_key)
+        t = l2b.Transformer(ck, synthetic_seed=SYNTH_SEED[workload], n_gpus=args.in_process)
+        data_desc = SYNTH_DESC
+        forced = teacher_tokens(positions + 1, ck.vocab_size)[1:]
     else:
         ck = shape_checkpoint(shape_key)
         t = l2b.Transformer(ck, synthetic_seed=SYNTH_SEED[workload], rank=rank, world_size=world,
@@ -414,7 +419,7 @@ def run_workload(workload, args, rank, world, dist, sync, flush, clock_index):
     }
     if world > 1 and forced is not None:
         out["parity"] = tp_parity(t, ck, workload, rank, device)
-    if world == 1 and forced is not None:
+    if world == 1 and forced is not None and args.in_process <= 1:
         # prompt prefill: the same positions as one prompt, on the device, no logits
         t.reset()
         t.prefill(np.concatenate([[1], forced[:positions - 1]]).astype(np.int32), 0, want_logits=False)
@@ -439,6 +444,9 @@ def main():
     ap.add_argument("--also", default="auto", help="comma list of extra workloads reported under 'also' (N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--positions", type=int, default=0, help="override positions per step (profiling runs only)")
+    ap.add_argument("--in-process", type=int, default=0, metavar="N",
+                    help="ONE process drives N GPUs (l2b_create(.., n_gpus=N), what the Zig CLI's --gpus uses) "
+                         "instead of one process per GPU; run without torchrun")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -455,7 +463,9 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
         dist.init_process_group("nccl")
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
+    if args.in_process > 1:
+        args.gpus = args.in_process
+    assert world == args.gpus or args.in_process > 1, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
     flush_buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
 
     def flush():
@@ -470,7 +480,7 @@ def main():
     clock_index = int(os.environ.get("LOCAL_RANK", 0))
     main_res = run_workload(workload, args, rank, world, dist, sync, flush, clock_index)
     also = {}
-    if world == 1 and args.also != "none":
+    if world == 1 and args.also != "none" and args.in_process <= 1:
         extra = ["stories15M", "stories110M"] if args.also == "auto" else [w for w in args.also.split(",") if w]
         for w in extra:
             if w != workload:
@@ -479,7 +489,7 @@ def main():
                                              "whole_step", "kernels", "positions", "data", "prefill") if k in r}
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and args.in_process <= 1:
             cpu = cpu_port_run(workload, budget_s=12.0)
             cpu.pop("seconds", None)
             try:
@@ -488,11 +498,11 @@ def main():
             except Exception:
                 pass
         line = {
-            "metric": "decode tokens/s", "value": main_res["value"], "unit": "tokens/s", "n_gpus": world,
+            "metric": "decode tokens/s", "value": main_res["value"], "unit": "tokens/s", "n_gpus": max(world, args.in_process),
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": main_res["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": main_res["data"],
-            "config": bench_config(workload, main_res["positions"], world),
+            "config": bench_config(workload, main_res["positions"], max(world, args.in_process)),
             "device_ms_per_step": main_res["device_ms_per_step"],
             "e2e": main_res["e2e"], "gpu_launches": main_res["launches"],
             "roofline": main_res["roofline"], "whole_step": main_res["whole_step"],
