@@ -368,3 +368,21 @@ def test_batched_prefill_on_bandwidth_bound_shapes(l2b, oracle):
         # decoding continues from the prefilled cache
         nxt = teacher_tokens(13, ck.vocab_size)[12]
         assert rel_err(b.forward(nxt, 12), a.forward(nxt, 12)) <= 1e-6
+
+
+def test_batched_prefill_long_prompt_with_attention_splits(l2b):
+    """A prompt longer than one attention split (> 256 positions on a 7B-shaped context): the batched
+    prefill's attention runs with timeline splits and a per-(position, head) last-arriver merge.  Checked
+    GPU against GPU: the same positions fed one by one (which the oracle tests pin) must give the same
+    logits afterwards, and a second chunked call must continue a partly filled cache."""
+    from llama2_zig_b200.checkpoint import shape_checkpoint
+    shape = (4096, 11008, 2, 32, 32, -32000, 2048)
+    toks = teacher_tokens(331, 32000)
+    with l2b.Transformer(shape_checkpoint(shape), synthetic_seed=3) as a, \
+            l2b.Transformer(shape_checkpoint(shape), synthetic_seed=3) as b:
+        for pos, tok in enumerate(toks):
+            want = a.forward(tok, pos)
+        assert b.prefill(toks[:200], 0, want_logits=False) is None      # 50 chunks of 4
+        got = b.prefill(toks[200:], 200)                                 # continues at pos 200, crosses 256; 131 = 32 chunks + 3
+        assert rel_err(got, want) <= 1e-6
+        assert int(np.argmax(got)) == int(np.argmax(want))
