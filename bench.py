@@ -366,6 +366,20 @@ def run_workload(workload, args, rank, world, dist, sync, flush, clock_index):
             _, h2d, d2h = e2e_run()
             sync()
             e2e_s.append(time.perf_counter() - t0)
+        # ---- same loop with the -t 0 fast path of the boundary (l2b_forward_argmax: the reference's argmax
+        # fused into the classifier epilogue, 4 bytes D2H per token instead of vocab * 4)
+        opt_am = GenOptions(0.0, 0.9, positions, 0, 1, 0, 0)
+        am_s = []
+        if forced is None:                       # free-running stream only (a forced prompt never takes the argmax path)
+            for _ in range(max(1, min(args.steps, 5))):
+                t.reset()
+                flush()
+                sync()
+                t0 = time.perf_counter()
+                rc = host_lib.l2h_generate(t.h, C.byref(t.cfg), C.byref(opt_am), None, 0, None, None, 0, C.byref(res))
+                assert rc == 0, rc
+                sync()
+                am_s.append(time.perf_counter() - t0)
         # ---- per-kernel roofline inside real steps (CUDA events between kernels, eager launches)
         t.reset()
         acc = {}
@@ -402,7 +416,8 @@ def run_workload(workload, args, rank, world, dist, sync, flush, clock_index):
         "launches": launches,
         "e2e": {"value": positions / e2e_tot, "unit": "tokens/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h),
-                "path": "C++ host loop (twin of src/main.zig:995-1042) -> l2b_forward(host logits) -> host argmax"},
+                "path": "C++ host loop (twin of src/main.zig:995-1042) -> l2b_forward(host logits) -> host argmax",
+                "device_argmax_variant": (positions / float(np.mean(am_s))) if am_s else None},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                      "frac": kernels[dom]["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "frac_of_8TBps_nominal": kernels[dom]["gbs"] / 8000.0, "peak_source": peak_src,
