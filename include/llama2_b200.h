@@ -186,8 +186,10 @@ int32_t l2b_abi_version(void);
  * floats written.                                                                          */
 int32_t l2b_read_state(l2b_ctx *ctx, int32_t which, float *dst, uint64_t n, uint64_t *n_out);
 
-/* Device time (ms, CUDA events on the context's stream) of the last forward/generate call,
- * and how many kernels of this library it launched.                                        */
+/* Device time (ms, CUDA events on the context's stream) of the last l2b_generate_argmax /
+ * l2b_prefill call (single steps are only timed when L2B_TIME_STEPS=1 is in the environment
+ * at create time: the two event records cost the end-to-end loop of a small model ~3 %), and how
+ * many kernels of this library the last call launched.                                      */
 int32_t l2b_last_timing(const l2b_ctx *ctx, float *device_ms, int32_t *kernel_launches);
 
 /* Checkpoint ingest of the last l2b_create on this context: wall time of the

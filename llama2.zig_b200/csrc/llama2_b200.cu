@@ -139,6 +139,7 @@ struct l2b_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool use_graphs = true;
     bool use_pdl = true;
+    bool time_steps = false;                 // L2B_TIME_STEPS=1: CUDA events around every single step (l2b_last_timing)
     int last_grid = 0;                       // grid of the most recent GEMV launch
     // tensor-parallel exchange over peer memory (world > 1).  One arena per rank holds every landing
     // area, so one IPC handle (or one UVA pointer) per rank is all the ranks trade at create time:
@@ -903,7 +904,7 @@ int enqueue_call(l2b_ctx *ctx, cudaStream_t st, int which) {
         if (rc) return rc;
         break;
     }
-    if (!loop)
+    if (!loop && ctx->world > 1)   // the error word can only be raised by a tensor-parallel peer wait
         L2B_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctl + CTL_WORDS, ctx->ctl, CTL_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
     return L2B_OK;
 }
@@ -1148,6 +1149,8 @@ int create_rank(l2b_ctx *ctx, const l2b_config *cfg, const Source &src, const fl
         ctx->use_graphs = !(env && env[0] == '1');
         const char *env2 = getenv("L2B_NO_PDL");
         ctx->use_pdl = !(env2 && env2[0] == '1');
+        const char *envts = getenv("L2B_TIME_STEPS");
+        ctx->time_steps = envts && envts[0] == '1';
         const char *env3 = getenv("L2B_GEMV8_MIN_BYTES");
         if (env3) ctx->gemv8_min_bytes = atoll(env3);
         const char *env4 = getenv("L2B_GEMV_BIG");
@@ -1402,12 +1405,17 @@ int finish_call(l2b_ctx *lead, const std::vector<l2b_ctx *> &ranks) {
 
 // run one step; which: G_LOGITS / G_ARGMAX_ONE / G_SAMPLE
 int run_step(l2b_ctx *lead, int token, int pos, int which, float temperature, float top_p) {
-    std::vector<l2b_ctx *> ranks = locals(lead);
-    for (l2b_ctx *ctx : ranks) {
-        L2B_CUDA(lead, cudaSetDevice(ctx->device));
+    // One step costs a small model ~90 us on the device, so every host call here is on the clock of
+    // the end-to-end loop: no per-step events unless asked for (L2B_TIME_STEPS=1), no allocation.
+    l2b_ctx *single[1] = {lead};
+    l2b_ctx *const *ranks = lead->members.empty() ? single : lead->members.data();
+    const size_t nranks = lead->members.empty() ? 1 : lead->members.size();
+    for (size_t i = 0; i < nranks; ++i) {
+        l2b_ctx *ctx = ranks[i];
+        if (nranks > 1 || i == 0) L2B_CUDA(lead, cudaSetDevice(ctx->device));
         fill_ctl(ctx, token, pos, 0, temperature, top_p);
         ctx->last_launches = 0;
-        if (ctx == lead) L2B_CUDA(lead, cudaEventRecord(ctx->ev0, ctx->stream));
+        if (ctx == lead && lead->time_steps) L2B_CUDA(lead, cudaEventRecord(ctx->ev0, ctx->stream));
         if (ctx->use_graphs) {
             L2B_CUDA(lead, cudaGraphLaunch(ctx->graphs[which], ctx->stream));
             ctx->last_launches = ctx->launches_per_step + (which == G_LOGITS ? 0 : 1);
@@ -1415,12 +1423,27 @@ int run_step(l2b_ctx *lead, int token, int pos, int which, float temperature, fl
             int rc = enqueue_call(ctx, ctx->stream, which);
             if (rc) { lead->err = ctx->err; return rc; }
         }
-        if (ctx == lead) L2B_CUDA(lead, cudaEventRecord(ctx->ev1, ctx->stream));
+        if (ctx == lead && lead->time_steps) L2B_CUDA(lead, cudaEventRecord(ctx->ev1, ctx->stream));
     }
-    int rc = finish_call(lead, ranks);
+    int rc = L2B_OK;
+    for (size_t i = 0; i < nranks; ++i) {
+        l2b_ctx *c = ranks[i];
+        if (nranks > 1) cudaSetDevice(c->device);
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess && rc == L2B_OK) {
+            lead->err = std::string("step failed: ") + cudaGetErrorString(e);
+            rc = L2B_ERR_CUDA;
+        }
+        if (c->h_ctl[CTL_WORDS + CTL_ERR] && rc == L2B_OK) {
+            lead->err = "tensor-parallel exchange timed out: a peer rank died or fell out of lockstep";
+            rc = L2B_ERR_COMM;
+        }
+    }
     if (rc) return rc;
-    L2B_CUDA(lead, cudaSetDevice(lead->device));
-    L2B_CUDA(lead, cudaEventElapsedTime(&lead->last_ms, lead->ev0, lead->ev1));
+    if (lead->time_steps) {
+        if (nranks > 1) L2B_CUDA(lead, cudaSetDevice(lead->device));
+        L2B_CUDA(lead, cudaEventElapsedTime(&lead->last_ms, lead->ev0, lead->ev1));
+    }
     if (pos + 1 > lead->n_appended) lead->n_appended = pos + 1;
     return L2B_OK;
 }
