@@ -139,3 +139,64 @@ def test_plan_partitions_every_sharded_tensor_exactly():
         assert total == 26_429_374_464 + replicated
     with pytest.raises(ValueError):
         tp_plan.shard_plan(shape_checkpoint("stories15M"), 0, 4)            # 6 kv heads % 4 != 0
+
+
+def _exchange_worker(rank, world, port, result_q):
+    """The data flow of the fused GEMV + all-reduce with gloo as the wire: every rank's
+    partial rows land in every rank's landing area [slot][source rank][dim] tagged with the step's
+    epoch; slice owners fold the ranks' rows into x in RANK ORDER.  Checks what the CUDA path relies on:
+    (1) every rank forms bit-identical x, (2) it equals the all-reduce within fp32 reordering noise,
+    (3) a step that skips a reduce point (prefill skips the classifier's) leaves stale epochs that are
+    never mistaken for this step's data."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(100 + rank)
+    dim, slots = 256, 4
+    landing = np.zeros((slots, world, dim), np.float32)
+    flags = np.zeros((slots, world), np.int64)           # epoch carried by the units of (slot, source rank)
+    x = np.ones(dim, np.float32)
+    ok = True
+    for epoch in range(1, 6):
+        skip_last = (epoch == 3)                         # a prefill-style step: the last reduce point is not consumed
+        for slot in range(slots):
+            partial = rng.standard_normal(dim).astype(np.float32)
+            gathered = [torch.zeros(dim) for _ in range(world)]
+            dist.all_gather(gathered, torch.from_numpy(partial))        # "posted stores into every rank's landing area"
+            for r in range(world):
+                landing[slot, r] = gathered[r].numpy()
+                flags[slot, r] = epoch
+            if skip_last and slot == slots - 1:
+                continue                                                # producer ran, nobody consumes this slot this step
+            assert np.all(flags[slot] == epoch)                         # the consumer only accepts this step's units
+            ref = torch.from_numpy(partial.copy())
+            dist.all_reduce(ref)
+            xn = x.copy()
+            for r in range(world):                                      # fixed rank order (tp_reduce_tail)
+                xn = (xn + landing[slot, r]).astype(np.float32)
+            ok = ok and np.allclose(xn, x + ref.numpy(), rtol=0, atol=1e-5)
+            x = xn
+        # stale epochs of a skipped reduce point are older than the next step's epoch
+        assert np.all(flags <= epoch)
+    digest = torch.tensor(np.frombuffer(x.tobytes(), dtype=np.uint8).astype(np.int64).sum())
+    both = [torch.zeros((), dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(both, digest)
+    bits = [torch.from_numpy(np.zeros(dim, np.float32)) for _ in range(world)]
+    dist.all_gather(bits, torch.from_numpy(x))
+    identical = all(np.array_equal(bits[0].numpy().view(np.uint32), b.numpy().view(np.uint32)) for b in bits)
+    if rank == 0:
+        result_q.put(bool(ok and identical))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_exchange_dataflow_is_rank_order_deterministic_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29750 + (os.getpid() % 200)
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
